@@ -1,0 +1,254 @@
+// b2048_capi.cu -- the extern "C" boundary of lib2048nn_b200.so (declared in include/b2048.h).
+// Plain pointers and sizes only; no torch types.  Every call enqueues on the caller's stream.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b2048.h"
+#include "engine_kernels.cuh"
+
+using namespace b2048;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *what, cudaError_t e) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+static int fail_msg(const char *what) {
+    snprintf(g_err, sizeof g_err, "%s", what);
+    return 2;
+}
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return fail(#call, e_); \
+    } while (0)
+
+#define N_COUNTERS 256
+
+struct b2048_ctx {
+    int device;
+    int num_sms;
+    uint16_t *fin_fwd, *fin_rev;
+    uint32_t *score;
+    uint8_t *moved_fwd, *moved_rev;
+    unsigned long long *counters;  // N_COUNTERS work cursors, one per in-flight launch
+    int *err_flag;
+    unsigned next_counter;
+    // root-search scratch (grown on demand outside of stream capture; see b2048_mcts_fixed)
+    uint64_t *rboard;
+    int64_t rboard_cap;
+};
+
+static Tables tables_of(const b2048_ctx *c) {
+    Tables t;
+    t.fin_fwd = c->fin_fwd;
+    t.fin_rev = c->fin_rev;
+    t.score = c->score;
+    return t;
+}
+
+extern "C" int b2048_abi_version(void) { return B2048_ABI_VERSION; }
+extern "C" const char *b2048_last_error(void) { return g_err; }
+
+extern "C" int b2048_create(int device, b2048_ctx **out) {
+    if (!out) return fail_msg("b2048_create: out is NULL");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail_msg("b2048_create: this library is built for sm_100a (Blackwell) only");
+    b2048_ctx *c = new b2048_ctx();
+    memset(c, 0, sizeof *c);
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->fin_fwd, 65536 * sizeof(uint16_t)));
+    CK(cudaMalloc(&c->fin_rev, 65536 * sizeof(uint16_t)));
+    CK(cudaMalloc(&c->score, 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&c->moved_fwd, 65536));
+    CK(cudaMalloc(&c->moved_rev, 65536));
+    CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
+    CK(cudaMemset(c->err_flag, 0, 2 * sizeof(int)));
+    build_tables_kernel<<<65536 / 256, 256>>>(c->fin_fwd, c->fin_rev, c->score, c->moved_fwd, c->moved_rev,
+                                              c->err_flag + 1);
+    CK(cudaGetLastError());
+    int mism = 0;
+    CK(cudaMemcpy(&mism, c->err_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (mism) return fail_msg("b2048_create: row-table invariants violated");
+    CK(cudaFuncSetAttribute(playout_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    *out = c;
+    return 0;
+}
+
+extern "C" int b2048_destroy(b2048_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaFree(c->fin_fwd);
+    cudaFree(c->fin_rev);
+    cudaFree(c->score);
+    cudaFree(c->moved_fwd);
+    cudaFree(c->moved_rev);
+    cudaFree(c->counters);
+    cudaFree(c->err_flag);
+    cudaFree(c->rboard);
+    delete c;
+    return 0;
+}
+
+extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
+
+/* device error flag: set when a spawn hit countzero == 0 (ValueError in the reference).
+ * Reads and clears it; synchronises `stream`. */
+extern "C" int b2048_take_error_flag(b2048_ctx *c, void *stream, int *out) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(out, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*out) CK(cudaMemsetAsync(c->err_flag, 0, sizeof(int), st));
+    return 0;
+}
+
+static inline int grid_for(long n, int threads, int cap) {
+    long g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+extern "C" int b2048_tables(b2048_ctx *c, uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score,
+                            uint8_t *moved_fwd, uint8_t *moved_rev, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fin_fwd) CK(cudaMemcpyAsync(fin_fwd, c->fin_fwd, 65536 * 2, cudaMemcpyDeviceToDevice, st));
+    if (fin_rev) CK(cudaMemcpyAsync(fin_rev, c->fin_rev, 65536 * 2, cudaMemcpyDeviceToDevice, st));
+    if (score) CK(cudaMemcpyAsync(score, c->score, 65536 * 4, cudaMemcpyDeviceToDevice, st));
+    if (moved_fwd) CK(cudaMemcpyAsync(moved_fwd, c->moved_fwd, 65536, cudaMemcpyDeviceToDevice, st));
+    if (moved_rev) CK(cudaMemcpyAsync(moved_rev, c->moved_rev, 65536, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int b2048_move_batch(b2048_ctx *c, const uint64_t *boards, const uint8_t *dirs, int dir_scalar,
+                                uint64_t *out_boards, uint32_t *out_score, uint8_t *out_moved, int64_t n,
+                                void *stream) {
+    if (n <= 0) return 0;
+    move_batch_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        tables_of(c), (const u64 *)boards, dirs, dir_scalar, (u64 *)out_boards, out_score, out_moved, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_board_ops(b2048_ctx *c, const uint64_t *boards, uint64_t *out_transpose,
+                               uint8_t *out_countzero, uint8_t *out_legal_mask, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    board_ops_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        tables_of(c), (const u64 *)boards, (u64 *)out_transpose, out_countzero, out_legal_mask, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_init_boards(b2048_ctx *c, uint64_t seed, uint64_t gid_base, uint64_t *out_boards,
+                                 int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    init_boards_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        seed, gid_base, (u64 *)out_boards, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_spawn_batch(b2048_ctx *c, const uint64_t *boards, uint64_t seed, const uint64_t *gids,
+                                 uint64_t gid_base, const uint32_t *k, uint32_t k_scalar, uint64_t *out_boards,
+                                 int32_t *err_flag, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    spawn_batch_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        (const u64 *)boards, seed, (const u64 *)gids, gid_base, k, k_scalar, (u64 *)out_boards, err_flag,
+        (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_rng_draws(b2048_ctx *c, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
+                               uint64_t *out, int64_t n, void *stream) {
+    if (n <= 0 || count <= 0) return 0;
+    rng_draws_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        seed, gid_base, first, count, (u64 *)out, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
+    p.tb = tables_of(c);
+    p.err_flag = c->err_flag;
+    unsigned slot = (c->next_counter++) % N_COUNTERS;
+    p.counter = c->counters + slot;
+    CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
+    int grid = grid_for(p.n, 1024, c->num_sms);
+    bool ludr = p.order[0] == 0 && p.order[1] == 1 && p.order[2] == 3 && p.order[3] == 2;
+    if (ludr)
+        playout_fixed_kernel<true><<<grid, 1024, 131072, st>>>(p);
+    else
+        playout_fixed_kernel<false><<<grid, 1024, 131072, st>>>(p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_playout_fixed(b2048_ctx *c, const uint64_t *start, const uint8_t *order4_host,
+                                   uint64_t seed, uint64_t gid_base, uint32_t spawn0, uint64_t *out_final,
+                                   uint32_t *out_score, uint32_t *out_moves, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    PlayParams p;
+    memset(&p, 0, sizeof p);
+    p.n = (long)n;
+    p.start = (const u64 *)start;
+    p.seed = seed;
+    p.gid_base = gid_base;
+    p.spawn0 = spawn0;
+    static const uint8_t ludr[4] = {0, 1, 3, 2};
+    for (int a = 0; a < 4; a++) p.order[a] = (order4_host ? order4_host[a] : ludr[a]) & 3;
+    p.out_final = (u64 *)out_final;
+    p.out_score = out_score;
+    p.out_moves = out_moves;
+    return launch_playout(c, p, (cudaStream_t)stream);
+}
+
+extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G, int number, int line_begin,
+                                int line_end, uint64_t seed, uint64_t eval_id_base, uint8_t *out_legal,
+                                uint32_t *out_rscore, uint32_t *out_lscore, uint32_t *out_lmoves,
+                                int64_t *out_logsum, int32_t *out_count, int32_t *out_minmov, void *stream) {
+    if (G <= 0) return 0;
+    if (number <= 0 || line_begin < 0 || line_end > number || line_begin > line_end)
+        return fail_msg("b2048_mcts_fixed: bad line range");
+    if (!out_legal || !out_rscore) return fail_msg("b2048_mcts_fixed: out_legal and out_rscore are required");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->rboard_cap < G * 4) {  // scratch for the boards after the root move; grows rarely
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c->rboard);
+        int64_t cap = G * 4 < 4096 ? 4096 : G * 4;
+        CK(cudaMalloc(&c->rboard, cap * sizeof(uint64_t)));
+        c->rboard_cap = cap;
+    }
+    root_moves_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
+                                                                       out_legal, out_rscore, (u64 *)c->rboard);
+    CK(cudaGetLastError());
+    if (line_begin == line_end) return 0;
+    PlayParams p;
+    memset(&p, 0, sizeof p);
+    p.root_mode = 1;
+    p.rboard = (const u64 *)c->rboard;
+    p.rlegal = out_legal;
+    p.rscore = out_rscore;
+    p.number = number;
+    p.line_begin = line_begin;
+    p.line_count = line_end - line_begin;
+    p.n = (long)G * 4 * p.line_count;
+    p.seed = seed;
+    p.gid_base = eval_id_base * 4ULL;
+    p.spawn0 = 1;
+    p.order[0] = 0, p.order[1] = 1, p.order[2] = 3, p.order[3] = 2;  // mcts.py:26
+    p.out_score = out_lscore;
+    p.out_moves = out_lmoves;
+    p.out_logsum = (long long *)out_logsum;
+    p.out_count = out_count;
+    p.out_minmov = out_minmov;
+    return launch_playout(c, p, st);
+}

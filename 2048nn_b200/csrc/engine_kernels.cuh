@@ -1,0 +1,330 @@
+// engine_kernels.cuh -- K1 (stateless move/spawn/board ops) and K2 (persistent fixed-order
+// playout + root-search reductions) for sm_100a.  Included by b2048_capi.cu.
+#pragma once
+#include "engine.cuh"
+
+namespace b2048 {
+
+// ---------------------------------------------------------------------------------------
+// Table build on the device (replaces board.py:134-148).  One thread per row.
+// ---------------------------------------------------------------------------------------
+__global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score, uint8_t *moved_fwd,
+                                    uint8_t *moved_rev, int *mismatch) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 65536) return;
+    u32 ff, sf, fr, sr;
+    row_slide(r, false, ff, sf);
+    row_slide(r, true, fr, sr);
+    fin_fwd[r] = (uint16_t)ff;
+    fin_rev[r] = (uint16_t)fr;
+    score[r] = sf;
+    moved_fwd[r] = ff != r;
+    moved_rev[r] = fr != r;
+    // invariants the playout kernel relies on: equal scores, mirrored finals
+    u32 mf, ms;
+    row_slide(mirror32(r) & 0xFFFFu, false, mf, ms);
+    if (sf != sr || (mirror32(mf) & 0xFFFFu) != fr) atomicAdd(mismatch, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 kernels
+// ---------------------------------------------------------------------------------------
+__global__ void move_batch_kernel(Tables tb, const u64 *__restrict__ boards, const uint8_t *__restrict__ dirs,
+                                  int dir_scalar, u64 *__restrict__ out_b, u32 *__restrict__ out_s,
+                                  uint8_t *__restrict__ out_m, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 x = boards[i];
+        int d = dirs ? dirs[i] : dir_scalar;
+        u32 s;
+        u64 f = move_exact(x, d, tb, s);
+        if (out_b) out_b[i] = f;
+        if (out_s) out_s[i] = s;
+        if (out_m) out_m[i] = f != x;
+    }
+}
+
+__global__ void board_ops_kernel(Tables tb, const u64 *__restrict__ boards, u64 *__restrict__ out_t,
+                                 uint8_t *__restrict__ out_cz, uint8_t *__restrict__ out_legal, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 x = boards[i];
+        if (out_t) out_t[i] = transpose(x);
+        if (out_cz) out_cz[i] = (uint8_t)countzero(x);
+        if (out_legal) {
+            int mask = 0;
+            for (int d = 0; d < 4; d++) {
+                u32 s;
+                mask |= (move_exact(x, d, tb, s) != x) << d;
+            }
+            out_legal[i] = (uint8_t)mask;
+        }
+    }
+}
+
+__global__ void init_boards_kernel(u64 seed, u64 gid_base, u64 *__restrict__ out, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = init_board(rng_key(seed, gid_base + (u64)i));
+}
+
+__global__ void spawn_batch_kernel(const u64 *__restrict__ boards, u64 seed, const u64 *__restrict__ gids,
+                                   u64 gid_base, const u32 *__restrict__ k, u32 k_scalar, u64 *__restrict__ out,
+                                   int *err_flag, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 b = boards[i];
+        if (countzero(b) == 0) {  // randrange(0): ValueError in the reference (board.py:87)
+            out[i] = 0;
+            if (err_flag) *err_flag = 1;
+            continue;
+        }
+        u64 key = rng_key(seed, gids ? gids[i] : gid_base + (u64)i);
+        u32 four;
+        out[i] = spawn_tile(b, rng_draw(key, B2048_INIT_DRAWS + (k ? k[i] : k_scalar)), four);
+    }
+}
+
+__global__ void rng_draws_kernel(u64 seed, u64 gid_base, u64 first, int count, u64 *__restrict__ out, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 key = rng_key(seed, gid_base + (u64)i);
+        for (int j = 0; j < count; j++) out[i * count + j] = rng_draw(key, first + j);
+    }
+}
+
+// root moves of G origins: legal flag, merge score and the moved board (mcts.py:21)
+__global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, long G, uint8_t *__restrict__ legal,
+                                  u32 *__restrict__ rscore, u64 *__restrict__ rboard) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * 4) return;
+    u64 x = origins[i >> 2];
+    u32 s;
+    u64 f = move_exact(x, (int)(i & 3), tb, s);
+    legal[i] = f != x;
+    rscore[i] = s;
+    rboard[i] = f;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: persistent fixed-order playout kernel.
+//
+// grid = #SMs, block = 1024 threads, one game per thread, 128 KB forward row table in shared
+// memory.  Each lane runs a flat loop {refill if needed; one move attempt cascade; spawn};
+// finished lanes refill from a global work counter (warp-aggregated atomic) so a warp never
+// waits for its longest game.  The L,U,D,R cascade is specialised: Up/Down work on the
+// transposed board (computed only when Left fails), Right/Down reuse the forward table through
+// mirror().  Scores come from the potential() closed form while no 32768+32768 annihilation is
+// possible; otherwise the game is finished on the exact table path.
+// ---------------------------------------------------------------------------------------
+struct PlayParams {
+    Tables tb;
+    // work definition
+    long n;                 // number of games (work items)
+    const u64 *start;       // FRESH/START mode: start boards (NULL or 0 entry -> fresh board)
+    const u64 *rboard;      // ROOT mode: [G*4] boards after the root move
+    const uint8_t *rlegal;  // ROOT mode: [G*4]
+    const u32 *rscore;      // ROOT mode: [G*4]
+    int root_mode;
+    int number, line_begin, line_count;  // ROOT mode: lines [line_begin, line_begin+line_count) of `number`
+    u64 seed, gid_base;                  // ROOT mode: gid_base = eval_id_base*4
+    u32 spawn0;
+    uint8_t order[4];
+    // outputs
+    u64 *out_final;
+    u32 *out_score;
+    u32 *out_moves;
+    long long *out_logsum;
+    int *out_count;
+    int *out_minmov;
+    // scratch
+    unsigned long long *counter;
+    int *err_flag;
+};
+
+// generic direction (any order): uniform code, no table for the reverse direction
+template <typename TablePtr>
+__device__ __forceinline__ u64 move_dir(u64 b, int d, TablePtr T) {
+    u64 x = (d & 1) ? transpose(b) : b;
+    x = (d & 2) ? slide_right(x, T) : slide_left(x, T);
+    return (d & 1) ? transpose(x) : x;
+}
+
+// Finish a game on the exact path (global tables, per-move scores): used when a 32768+32768
+// annihilation is possible, i.e. never in practice but required for bit-exactness.
+struct ExactResult {
+    u64 b;
+    u32 count, score;
+    int err;
+};
+__device__ __noinline__ ExactResult finish_exact(const PlayParams &p, u64 b, u64 key, u32 count, u32 score) {
+    ExactResult r;
+    r.err = 0;
+    for (;;) {
+        bool adv = false;
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {
+            u32 s;
+            u64 f = move_exact(b, p.order[a], p.tb, s);
+            if (f != b) {
+                if (countzero(f) == 0) {  // total annihilation -> randrange(0) in the reference
+                    r.err = 1;
+                    adv = false;
+                    break;
+                }
+                u32 four;
+                b = spawn_tile(f, rng_draw(key, B2048_INIT_DRAWS + p.spawn0 + count), four);
+                score += s;
+                count++;
+                adv = true;
+                break;
+            }
+        }
+        if (!adv) break;
+    }
+    r.b = b;
+    r.count = count;
+    r.score = score;
+    return r;
+}
+
+template <bool LUDR>
+__global__ void __launch_bounds__(1024, 1) playout_fixed_kernel(const PlayParams p) {
+    extern __shared__ __align__(16) uint16_t sT[];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tb.fin_fwd);
+        uint4 *dst = reinterpret_cast<uint4 *>(sT);
+        for (int i = threadIdx.x; i < 65536 * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31;
+    const long total_threads = (long)gridDim.x * blockDim.x;
+    long item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // first game: static assignment
+    bool first = true;
+
+    bool have = false;
+    u64 b = 0, key = 0;
+    u32 count = 0, n4 = 0, pot0 = 0, limit = 0, rs = 0;
+    long slot = 0;  // output index of the current game
+
+    for (;;) {
+        if (!have) {
+            // ---- refill: lanes here may be any subset of the warp --------------------------
+            if (!first) {
+                unsigned m = __activemask();
+                int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(m));
+                base = __shfl_sync(m, base, leader);
+                item = total_threads + (long)base + __popc(m & ((1u << lane) - 1));
+            }
+            first = false;
+            if (item >= p.n) break;
+            slot = item;
+            count = 0;
+            n4 = 0;
+            rs = 0;
+            bool skip = false;
+            if (p.root_mode) {
+                long r = item / p.line_count;  // root index g*4+i
+                int j = p.line_begin + (int)(item - r * p.line_count);
+                slot = r * p.number + j;
+                if (!p.rlegal[r]) {
+                    skip = true;
+                } else {
+                    key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
+                    u64 rb = p.rboard[r];
+                    rs = p.rscore[r];
+                    if (countzero(rb) == 0) {
+                        *p.err_flag = 1;
+                        skip = true;
+                    } else {
+                        u32 four;
+                        b = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);  // mcts.py:23
+                    }
+                }
+            } else {
+                key = rng_key(p.seed, p.gid_base + (u64)item);
+                u64 s0 = p.start ? p.start[item] : 0ULL;
+                b = s0 ? s0 : init_board(key);  // board.py:205 `if not board`
+            }
+            if (skip) {
+                if (p.out_final) p.out_final[slot] = 0;
+                if (p.out_score) p.out_score[slot] = 0;
+                if (p.out_moves) p.out_moves[slot] = 0;
+                continue;
+            }
+            pot0 = potential(b);
+            u32 ts = tile_sum(b);
+            limit = ts >= 65536u ? 0u : ((65536u - ts + 3u) >> 2);  // moves that cannot annihilate
+            have = true;
+        }
+
+        // ---- one move: first legal direction of the priority order ----------------------
+        u64 nb;
+        bool moved;
+        if (LUDR) {
+            nb = slide_left(b, sT);  // Left
+            moved = nb != b;
+            if (!moved) {
+                u64 bt = transpose(b);
+                u64 nt = slide_left(bt, sT);  // Up
+                if (nt == bt) nt = slide_right(bt, sT);  // Down
+                if (nt != bt) {
+                    nb = transpose(nt);
+                    moved = true;
+                } else {
+                    nb = slide_right(b, sT);  // Right
+                    moved = nb != b;
+                }
+            }
+        } else {
+            moved = false;
+            nb = b;
+#pragma unroll 1
+            for (int a = 0; a < 4 && !moved; a++) {
+                nb = move_dir(b, p.order[a], sT);
+                moved = nb != b;
+            }
+        }
+
+        if (moved && count < limit) {
+            u32 four;
+            b = spawn_tile(nb, rng_draw(key, B2048_INIT_DRAWS + p.spawn0 + count), four);
+            n4 += four;
+            count++;
+            continue;
+        }
+
+        // ---- game over (or hand-over to the exact path) ----------------------------------
+        u32 score = potential(b) - pot0 - 4u * n4;
+        if (moved) {  // count >= limit: annihilation possible from here on
+            ExactResult r = finish_exact(p, b, key, count, score);
+            b = r.b;
+            count = r.count;
+            score = r.score;
+            if (r.err) *p.err_flag = 1;
+        }
+        if (p.out_final) p.out_final[slot] = b;
+        if (p.out_score) p.out_score[slot] = score;
+        if (p.out_moves) p.out_moves[slot] = count;
+        if (p.root_mode) {
+            long r = slot / p.number;
+            if (p.out_logsum) {
+                double t = log10((double)score + (double)rs + 1.0);  // mcts.py:31
+                long long q = __double2ll_rn(ldexp(t, 40));
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
+            }
+            if (p.out_count) atomicAdd(p.out_count + r, 1);
+            if (p.out_minmov) atomicMin(p.out_minmov + r, (int)count);
+        }
+        have = false;
+    }
+}
+
+}  // namespace b2048

@@ -1,0 +1,125 @@
+"""Tensor-level host API over the C ABI: device tensors in, device tensors out, no syncs.
+
+Boards are torch.int64 tensors holding the uint64 bit pattern (nibble k = cell (k/4, k%4)).
+Each function names the reference code it replaces (file:line in fqjin/2048NN).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+LUDR = (0, 1, 3, 2)  # board.py:214
+
+
+def _dev(t):
+    return t.device
+
+
+def tables(device="cuda"):
+    """Row tables built on the device (board.py:104-148): dict of device tensors."""
+    d = torch.device(device)
+    out = dict(fin_fwd=torch.empty(65536, dtype=torch.int16, device=d),
+               fin_rev=torch.empty(65536, dtype=torch.int16, device=d),
+               score=torch.empty(65536, dtype=torch.int32, device=d),
+               moved_fwd=torch.empty(65536, dtype=torch.uint8, device=d),
+               moved_rev=torch.empty(65536, dtype=torch.uint8, device=d))
+    L.check(L.load_library().b2048_tables(L.ctx(d), L.ptr(out["fin_fwd"]), L.ptr(out["fin_rev"]), L.ptr(out["score"]),
+                                          L.ptr(out["moved_fwd"]), L.ptr(out["moved_rev"]), L.stream_ptr(d)))
+    return out
+
+
+def move_batch(boards, dirs):
+    """board.py:151-189 move() for N boards.  dirs: int or uint8 tensor[N].
+    -> (boards int64[N], score int32[N], moved uint8[N])"""
+    d = _dev(boards)
+    n = boards.numel()
+    ob = torch.empty_like(boards)
+    os_ = torch.empty(n, dtype=torch.int32, device=d)
+    om = torch.empty(n, dtype=torch.uint8, device=d)
+    if isinstance(dirs, torch.Tensor):
+        dirs = dirs.to(device=d, dtype=torch.uint8).contiguous()
+        dp, ds = L.ptr(dirs), 0
+    else:
+        dp, ds = None, int(dirs)
+    L.check(L.load_library().b2048_move_batch(L.ctx(d), L.ptr(boards), dp, ds, L.ptr(ob), L.ptr(os_), L.ptr(om), n,
+                                              L.stream_ptr(d)))
+    return ob, os_, om
+
+
+def board_ops(boards, transpose=True, countzero=True, legal=True):
+    """board.py:46-65 transpose / countzero, and the legal-move mask, for N boards."""
+    d = _dev(boards)
+    n = boards.numel()
+    t = torch.empty_like(boards) if transpose else None
+    cz = torch.empty(n, dtype=torch.uint8, device=d) if countzero else None
+    lg = torch.empty(n, dtype=torch.uint8, device=d) if legal else None
+    L.check(L.load_library().b2048_board_ops(L.ctx(d), L.ptr(boards), L.ptr(t), L.ptr(cz), L.ptr(lg), n, L.stream_ptr(d)))
+    return t, cz, lg
+
+
+def init_boards(n, seed, gid_base=0, device="cuda"):
+    """board.py:68-82 generate_init_tiles for games gid_base..gid_base+n-1."""
+    d = torch.device(device)
+    out = torch.empty(n, dtype=torch.int64, device=d)
+    L.check(L.load_library().b2048_init_boards(L.ctx(d), seed, gid_base, L.ptr(out), n, L.stream_ptr(d)))
+    return out
+
+
+def spawn_batch(boards, seed, gids=None, gid_base=0, k=0):
+    """board.py:85-101 generate_tile: spawn number k of stream (seed, gid) on each board.
+    Returns (boards, err) where err is an int32[1] device flag (countzero == 0 somewhere)."""
+    d = _dev(boards)
+    n = boards.numel()
+    out = torch.empty_like(boards)
+    err = torch.zeros(1, dtype=torch.int32, device=d)
+    if isinstance(k, torch.Tensor):
+        k = k.to(device=d, dtype=torch.int32).contiguous()
+        kp, ks = L.ptr(k), 0
+    else:
+        kp, ks = None, int(k)
+    L.check(L.load_library().b2048_spawn_batch(L.ctx(d), L.ptr(boards), seed, L.ptr(gids), gid_base, kp, ks, L.ptr(out),
+                                               L.ptr(err), n, L.stream_ptr(d)))
+    return out, err
+
+
+def rng_draws(n, seed, gid_base, first, count, device="cuda"):
+    d = torch.device(device)
+    out = torch.empty((n, count), dtype=torch.int64, device=d)
+    L.check(L.load_library().b2048_rng_draws(L.ctx(d), seed, gid_base, first, count, L.ptr(out), n, L.stream_ptr(d)))
+    return out
+
+
+def playout_fixed(n, seed, gid_base=0, start=None, order=LUDR, spawn0=0, device="cuda", out=None):
+    """K2: n fixed-order games to the end in one persistent kernel (board.py:192-225, 306-315).
+    -> (final int64[n], score int32[n], moves int32[n]) device tensors, indexed by game."""
+    d = torch.device(device) if start is None else _dev(start)
+    if out is None:
+        out = (torch.empty(n, dtype=torch.int64, device=d), torch.empty(n, dtype=torch.int32, device=d),
+               torch.empty(n, dtype=torch.int32, device=d))
+    o = (C.c_uint8 * 4)(*[int(x) & 3 for x in order])
+    L.check(L.load_library().b2048_playout_fixed(L.ctx(d), L.ptr(start), o, seed, gid_base, spawn0, L.ptr(out[0]),
+                                                 L.ptr(out[1]), L.ptr(out[2]), n, L.stream_ptr(d)))
+    return out
+
+
+def mcts_fixed_lines(origins, number, seed, eval_id_base=0, line_begin=0, line_end=None, per_line=True, fused=True):
+    """Root search lines for G origins (mcts.py:4-103).  Returns a dict of device tensors:
+    legal u8[G,4], rscore i32[G,4], and (per_line) lscore/lmoves i32[G,4,number],
+    (fused) logsum i64[G,4] (fixed point 2^-40), count i32[G,4], minmov i32[G,4]."""
+    d = _dev(origins)
+    G = origins.numel()
+    line_end = number if line_end is None else line_end
+    r = dict(legal=torch.empty((G, 4), dtype=torch.uint8, device=d), rscore=torch.empty((G, 4), dtype=torch.int32, device=d))
+    if per_line:
+        r["lscore"] = torch.zeros((G, 4, number), dtype=torch.int32, device=d)
+        r["lmoves"] = torch.zeros((G, 4, number), dtype=torch.int32, device=d)
+    if fused:
+        r["logsum"] = torch.zeros((G, 4), dtype=torch.int64, device=d)
+        r["count"] = torch.zeros((G, 4), dtype=torch.int32, device=d)
+        r["minmov"] = torch.full((G, 4), 2**31 - 1, dtype=torch.int32, device=d)
+    L.check(L.load_library().b2048_mcts_fixed(
+        L.ctx(d), L.ptr(origins), G, number, line_begin, line_end, seed, eval_id_base, L.ptr(r["legal"]), L.ptr(r["rscore"]),
+        L.ptr(r.get("lscore")), L.ptr(r.get("lmoves")), L.ptr(r.get("logsum")), L.ptr(r.get("count")), L.ptr(r.get("minmov")),
+        L.stream_ptr(d)))
+    return r

@@ -1,0 +1,127 @@
+/*
+ * b2048.h -- C ABI of lib2048nn_b200.so: the B200 (sm_100a) playout engine for fqjin/2048NN.
+ *
+ * The reference has no FFI of its own (it is pure Python); this header is the boundary a
+ * maintainer binds instead of the Python hot loops.  Each entry point names the reference
+ * code it replaces (file:line into the reference repo).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is
+ *     enqueued on it, nothing synchronises the host, nothing allocates after b2048_create
+ *     (one exception: b2048_mcts_* grow a root-board scratch buffer when G exceeds every
+ *     earlier call's G; b2048_take_error_flag is the one call that synchronises);
+ *   - return value: 0 = ok, non-zero = error (b2048_last_error() gives the text);
+ *   - boards are uint64: nibble k (bits 4k..4k+3) is the tile exponent of cell
+ *     (row k/4, col k%4), nibble 0 = top-left (board.py:23-33, 228-233);
+ *   - directions: 0 Left, 1 Up, 2 Right, 3 Down, taken mod 4 (board.py:151-189);
+ *   - scores are uint32 (a move scores at most 524,288; real games stay far below 2^32).
+ *
+ * RNG protocol (replaces CPython's MT19937 `randrange`, board.py:6,70-98).
+ *   Every game owns a counter-based stream:
+ *       mix64(z): z=(z^(z>>30))*0xBF58476D1CE4E5B9; z=(z^(z>>27))*0x94D049BB133111EB; z^(z>>31)
+ *       key       = mix64(mix64(seed + G) ^ (game_id*0xD1342543DE82EF95 + 1)),  G = 0x9E3779B97F4A7C15
+ *       draw(i)   = mix64(key + (i+1)*G)                      (64 bits = two 32-bit words: hi, lo)
+ *       randrange(n) := (word * n) >> 32
+ *   generate_init_tiles (board.py:68-82) consumes words 0.. of draws 0..7 in the reference's
+ *   call order (pos1, pos2 [redrawn while equal], tile1, tile2).  The k-th generate_tile of a
+ *   game (board.py:85-101) uses draw 8+k: hi word -> position, lo word -> randrange(10).
+ *   Root-search line j of root move i of evaluation e (mcts.py:23, mcts_nn.py:22) is game
+ *   game_id = (e*4 + i)*number + j; its first spawn is k = 0.
+ */
+#ifndef B2048_H
+#define B2048_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2048_ctx b2048_ctx;
+
+#define B2048_ABI_VERSION 1
+
+/* reduction modes of b2048_mcts_fixed / b2048_mcts_nn */
+#define B2048_MODE_MEANLOG 0 /* mcts.py:4-34   mcts_fixed (README: mcts_fixed_batch) */
+#define B2048_MODE_MEDIAN 1  /* mcts.py:37-70  mcts_fixed_moves */
+#define B2048_MODE_MIN 2     /* mcts.py:73-103 mcts_fixed_min; mcts_nn.py:4-43 mcts_nn */
+
+/* fixed-point scale of the fused log10 sums (order-independent, shard-invariant) */
+#define B2048_LOGSUM_FRAC_BITS 40
+
+int b2048_abi_version(void);
+const char *b2048_last_error(void);
+
+/* Per-device context: row tables in device memory (replaces the merge_table /
+ * merge_table_rev build + pickle cache, board.py:104-148) and launch scratch. */
+int b2048_create(int device, b2048_ctx **out);
+int b2048_destroy(b2048_ctx *ctx);
+int b2048_num_sms(const b2048_ctx *ctx);
+
+/* Device error flag: set when a spawn met countzero == 0 (the reference raises ValueError from
+ * randrange(0), board.py:87).  Reads and clears it into *out_host; synchronises `stream`. */
+int b2048_take_error_flag(b2048_ctx *ctx, void *stream, int *out_host);
+
+/* Row tables as built on the device: fin_fwd/fin_rev u16[65536], score u32[65536] (identical
+ * for both tables), moved_fwd/moved_rev u8[65536].  Any pointer may be NULL.  (board.py:138-148) */
+int b2048_tables(b2048_ctx *ctx, uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score, uint8_t *moved_fwd,
+                 uint8_t *moved_rev, void *stream);
+
+/* K1: move() for N boards (board.py:151-189).  dirs == NULL -> every board uses dir_scalar. */
+int b2048_move_batch(b2048_ctx *ctx, const uint64_t *boards, const uint8_t *dirs, int dir_scalar,
+                     uint64_t *out_boards, uint32_t *out_score, uint8_t *out_moved, int64_t n, void *stream);
+
+/* transpose (board.py:46-54), countzero (board.py:57-65; 16 empties -> 0) and the legal-move
+ * mask (bit d set when move(board,d) moves) for N boards.  Output pointers may be NULL. */
+int b2048_board_ops(b2048_ctx *ctx, const uint64_t *boards, uint64_t *out_transpose, uint8_t *out_countzero,
+                    uint8_t *out_legal_mask, int64_t n, void *stream);
+
+/* generate_init_tiles (board.py:68-82) for games gid_base..gid_base+n-1 of `seed`. */
+int b2048_init_boards(b2048_ctx *ctx, uint64_t seed, uint64_t gid_base, uint64_t *out_boards, int64_t n,
+                      void *stream);
+
+/* generate_tile (board.py:85-101): out[g] = spawn number k[g] (k == NULL -> k_scalar) of stream
+ * (seed, gids[g]) (gids == NULL -> gid_base+g) placed on boards[g].  A board with
+ * countzero == 0 (randrange(0) -> ValueError in the reference) yields out = 0 and sets
+ * err_flag[0] = 1 when err_flag != NULL. */
+int b2048_spawn_batch(b2048_ctx *ctx, const uint64_t *boards, uint64_t seed, const uint64_t *gids,
+                      uint64_t gid_base, const uint32_t *k, uint32_t k_scalar, uint64_t *out_boards,
+                      int32_t *err_flag, int64_t n, void *stream);
+
+/* raw stream words for parity tests: out[g*count + j] = draw(first + j) of stream (seed, gid_base+g) */
+int b2048_rng_draws(b2048_ctx *ctx, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
+                    uint64_t *out, int64_t n, void *stream);
+
+/* K2: N fixed-order games played to the end inside one persistent kernel
+ * (board.py:192-225 play_fixed; board.py:246-277 + 306-315 BoardArray.move_batch /
+ * play_fixed_batch iterated to termination).
+ *   start      N boards, or NULL for fresh boards (generate_init_tiles); a 0 entry also means
+ *              "fresh board" (board.py:205 `if not board`)
+ *   order4     HOST pointer to 4 direction indices, NULL = (0,1,3,2) = L,U,D,R (board.py:214)
+ *   spawn0     index of the first spawn draw (0 for whole games)
+ * outputs (each may be NULL), indexed by game: final board, score gained, accepted moves. */
+int b2048_playout_fixed(b2048_ctx *ctx, const uint64_t *start, const uint8_t *order4_host, uint64_t seed,
+                        uint64_t gid_base, uint32_t spawn0, uint64_t *out_final, uint32_t *out_score,
+                        uint32_t *out_moves, int64_t n, void *stream);
+
+/* Root search with fixed-order playouts for G origins x 4 root moves x `number` lines
+ * (mcts.py:4-103).  Lines [line_begin, line_end) of every root move are played by this call
+ * (a rank plays its shard; the union over ranks is [0, number)).
+ *   out_legal   u8[G*4]   move(origin, i) moved
+ *   out_rscore  u32[G*4]  root-move merge score s (mcts.py:21,31)
+ *   out_lscore  u32[G*4*number]  per-line playout score (BoardArray scores start at 0), or NULL
+ *   out_lmoves  u32[G*4*number]  per-line accepted moves L_j after the first spawn, or NULL
+ *   out_logsum  i64[G*4]  ACCUMULATED: sum over the lines played of
+ *                         round(log10(score + s + 1) * 2^B2048_LOGSUM_FRAC_BITS), or NULL
+ *   out_count   i32[G*4]  ACCUMULATED: lines played, or NULL
+ *   out_minmov  i32[G*4]  ACCUMULATED (min): min_j L_j (caller initialises to INT32_MAX), or NULL
+ * Accumulated outputs are what an allreduce (SUM / SUM / MIN) combines across ranks. */
+int b2048_mcts_fixed(b2048_ctx *ctx, const uint64_t *origins, int64_t G, int number, int line_begin,
+                     int line_end, uint64_t seed, uint64_t eval_id_base, uint8_t *out_legal,
+                     uint32_t *out_rscore, uint32_t *out_lscore, uint32_t *out_lmoves, int64_t *out_logsum,
+                     int32_t *out_count, int32_t *out_minmov, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2048_H */
