@@ -35,6 +35,7 @@ _SIGS = {
     "b2048_board_ops": (C.c_int, [P, P, P, P, P, i64, P]),
     "b2048_init_boards": (C.c_int, [P, u64, u64, P, i64, P]),
     "b2048_spawn_batch": (C.c_int, [P, P, u64, P, u64, P, u32, P, P, i64, P]),
+    "b2048_policy_step": (C.c_int, [P, P, P, u64, P, u64, P, P, P, P, i64, P]),
     "b2048_rng_draws": (C.c_int, [P, u64, u64, u64, C.c_int, P, i64, P]),
     "b2048_playout_fixed": (C.c_int, [P, P, P, u64, u64, u32, P, P, P, i64, P]),
     "b2048_mcts_fixed": (C.c_int, [P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P, P, P]),
@@ -69,10 +70,15 @@ def check(rc):
         raise B2048Error(load_library().b2048_last_error().decode())
 
 
-def ctx(device=None):
-    """Per-device engine context (row tables are built on the device at creation)."""
+def require_cuda():
     if not torch.cuda.is_available():
         raise B2048Error("2048nn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    load_library()
+
+
+def ctx(device=None):
+    """Per-device engine context (row tables are built on the device at creation)."""
+    require_cuda()
     dev = torch.cuda.current_device() if device is None else torch.device(device).index
     if dev is None:
         dev = torch.cuda.current_device()
@@ -106,6 +112,7 @@ def to_i64(x):
 
 
 def boards_to_device(x, device="cuda"):
+    require_cuda()
     if isinstance(x, torch.Tensor):
         if x.dtype != torch.int64:
             raise TypeError("board tensors must be int64 bit patterns")

@@ -176,6 +176,19 @@ extern "C" int b2048_rng_draws(b2048_ctx *c, uint64_t seed, uint64_t gid_base, u
     return 0;
 }
 
+extern "C" int b2048_policy_step(b2048_ctx *c, const uint64_t *boards, const uint8_t *prio, uint64_t seed,
+                                 const uint64_t *gids, uint64_t gid_base, const uint32_t *k, uint64_t *out_boards,
+                                 uint32_t *out_gain, uint8_t *out_moved, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    if (!boards || !prio || !k || !out_boards || !out_gain || !out_moved)
+        return fail_msg("b2048_policy_step: NULL argument");
+    policy_step_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        tables_of(c), (const u64 *)boards, prio, seed, (const u64 *)gids, gid_base, k, (u64 *)out_boards, out_gain,
+        out_moved, c->err_flag, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     p.tb = tables_of(c);
     p.err_flag = c->err_flag;

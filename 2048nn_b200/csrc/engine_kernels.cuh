@@ -97,6 +97,43 @@ __global__ void rng_draws_kernel(u64 seed, u64 gid_base, u64 first, int count, u
     }
 }
 
+// One BoardArray.move_batch step (board.py:246-277): per game, the first legal direction of
+// its own priority row, then generate_tile.  Games that cannot move keep their board.
+__global__ void policy_step_kernel(Tables tb, const u64 *__restrict__ boards, const uint8_t *__restrict__ prio,
+                                   u64 seed, const u64 *__restrict__ gids, u64 gid_base, const u32 *__restrict__ k,
+                                   u64 *__restrict__ out_b, u32 *__restrict__ out_gain, uint8_t *__restrict__ out_moved,
+                                   int *err_flag, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 b = boards[i];
+        u32 pr = *reinterpret_cast<const u32 *>(prio + 4 * i);
+        u64 nb = b;
+        u32 gain = 0;
+        bool moved = false;
+#pragma unroll 1
+        for (int a = 0; a < 4 && !moved; a++) {
+            nb = move_exact(b, (pr >> (8 * a)) & 3, tb, gain);
+            moved = nb != b;
+        }
+        if (moved) {
+            if (countzero(nb) == 0) {
+                *err_flag = 1;
+                nb = 0;
+            } else {
+                u64 key = rng_key(seed, gids ? gids[i] : gid_base + (u64)i);
+                u32 four;
+                nb = spawn_tile(nb, rng_draw(key, B2048_INIT_DRAWS + k[i]), four);
+            }
+        } else {
+            gain = 0;
+        }
+        out_b[i] = nb;
+        out_gain[i] = gain;
+        out_moved[i] = moved;
+    }
+}
+
 // root moves of G origins: legal flag, merge score and the moved board (mcts.py:21)
 __global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, long G, uint8_t *__restrict__ legal,
                                   u32 *__restrict__ rscore, u64 *__restrict__ rboard) {

@@ -60,6 +60,7 @@ def board_ops(boards, transpose=True, countzero=True, legal=True):
 
 def init_boards(n, seed, gid_base=0, device="cuda"):
     """board.py:68-82 generate_init_tiles for games gid_base..gid_base+n-1."""
+    L.require_cuda()
     d = torch.device(device)
     out = torch.empty(n, dtype=torch.int64, device=d)
     L.check(L.load_library().b2048_init_boards(L.ctx(d), seed, gid_base, L.ptr(out), n, L.stream_ptr(d)))
@@ -83,6 +84,19 @@ def spawn_batch(boards, seed, gids=None, gid_base=0, k=0):
     return out, err
 
 
+def policy_step(boards, prio, seed, k, gids=None, gid_base=0):
+    """board.py:246-303: one move_batch step with per-game priority rows prio uint8[N,4].
+    -> (boards int64[N], gain int32[N], moved uint8[N])"""
+    d = _dev(boards)
+    n = boards.numel()
+    ob = torch.empty_like(boards)
+    gain = torch.empty(n, dtype=torch.int32, device=d)
+    moved = torch.empty(n, dtype=torch.uint8, device=d)
+    L.check(L.load_library().b2048_policy_step(L.ctx(d), L.ptr(boards), L.ptr(prio), seed, L.ptr(gids), gid_base, L.ptr(k),
+                                               L.ptr(ob), L.ptr(gain), L.ptr(moved), n, L.stream_ptr(d)))
+    return ob, gain, moved
+
+
 def rng_draws(n, seed, gid_base, first, count, device="cuda"):
     d = torch.device(device)
     out = torch.empty((n, count), dtype=torch.int64, device=d)
@@ -93,6 +107,7 @@ def rng_draws(n, seed, gid_base, first, count, device="cuda"):
 def playout_fixed(n, seed, gid_base=0, start=None, order=LUDR, spawn0=0, device="cuda", out=None):
     """K2: n fixed-order games to the end in one persistent kernel (board.py:192-225, 306-315).
     -> (final int64[n], score int32[n], moves int32[n]) device tensors, indexed by game."""
+    L.require_cuda()
     d = torch.device(device) if start is None else _dev(start)
     if out is None:
         out = (torch.empty(n, dtype=torch.int64, device=d), torch.empty(n, dtype=torch.int32, device=d),
@@ -123,3 +138,32 @@ def mcts_fixed_lines(origins, number, seed, eval_id_base=0, line_begin=0, line_e
         L.ptr(r.get("lscore")), L.ptr(r.get("lmoves")), L.ptr(r.get("logsum")), L.ptr(r.get("count")), L.ptr(r.get("minmov")),
         L.stream_ptr(d)))
     return r
+
+
+class HostPlayout:
+    """Host-buffer front end of K2 for large batches: pinned host start boards in, pinned host
+    (final, score, moves) out, with the H2D / D2H copies enqueued on the same stream as the
+    kernel.  Buffers are allocated once and reused (what a caller streaming batches would do)."""
+
+    def __init__(self, n, device="cuda"):
+        L.require_cuda()
+        self.n = n
+        self.device = torch.device(device)
+        self.d_start = torch.empty(n, dtype=torch.int64, device=self.device)
+        self.d_out = (torch.empty(n, dtype=torch.int64, device=self.device),
+                      torch.empty(n, dtype=torch.int32, device=self.device),
+                      torch.empty(n, dtype=torch.int32, device=self.device))
+        self.h_out = (torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
+                      torch.empty(n, dtype=torch.int32).pin_memory())
+        self.h2d_bytes = n * 8
+        self.d2h_bytes = n * 16
+
+    def __call__(self, h_start, seed, gid_base=0, order=LUDR):
+        """h_start: pinned int64[n] host tensor of start boards (0 = fresh board).  Returns the
+        pinned host tensors (final, score, moves); synchronises the stream before returning."""
+        self.d_start.copy_(h_start, non_blocking=True)
+        playout_fixed(self.n, seed, gid_base, start=self.d_start, order=order, out=self.d_out)
+        for h, d in zip(self.h_out, self.d_out):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.h_out

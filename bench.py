@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- playout moves/sec of the B200 engine (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--impl ours|reference]
+
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL).
+A "step" is one pass of the hot path (play_fixed_batch: every game played to termination
+inside one persistent kernel) over one batch of `--games` synthetic fresh start boards per GPU.
+Per-GPU work is fixed as N grows ("weak"); the path shards by game with no data-path
+collective -- ranks only exchange their move counts and times for the report.
+
+`--impl reference` times the CPU implementation of the same path on the box's host cores.  The
+reference is pure Python (no compiled part), so the arm runs the C restatement in oracle/
+(kind "port") on all host threads -- a faster baseline than the Python original.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "playout moves/sec (fixed-order, play_fixed_batch to termination)"
+UNIT = "moves/s"
+INSTR_PER_MOVE = 250.0  # algorithmic thread-instructions per accepted move
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        hi = [x for x in sm if mx and x > 0.5 * mx] or sm  # samples under load
+        med = hi[len(hi) // 2] if hi else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(target_seconds, nthreads):
+    """Oracle port (C) on the host: play_fixed_batch on a bounded sample -> (moves/s, sample str)."""
+    from oracle import oracle
+
+    oracle.lib()
+    t0 = time.perf_counter()
+    _, _, c = oracle.play_fixed_batch(20000, 99, 0, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    rate = float(c.sum()) / dt
+    n = int(max(20000, min(20_000_000, rate * target_seconds / 225.0)))
+    t0 = time.perf_counter()
+    _, _, c = oracle.play_fixed_batch(n, 100, 0, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return float(c.sum()) / dt, f"{n} fresh fixed-order games ({int(c.sum())} moves) in {dt:.2f}s wall"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    cores = oracle.lib().orc_num_threads()
+    workload = workload_name(args.games)
+    for _ in range(args.warmup):
+        cpu_port_rate(0.3, cores)
+    rates, sample = [], ""
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, sample = cpu_port_rate(max(1.0, min(8.0, 60.0 / max(1, args.steps))), cores)
+        rates.append(r)
+    wall = time.perf_counter() - t_all
+    v = sum(rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload, "note": "reference is pure Python; timed here as its C restatement "
+                   "(oracle/b2048_oracle.c) on all host threads, each step a bounded sample of the workload"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(games):
+    return f"play_fixed_batch: {games} concurrent fixed-order (L,U,D,R) games per GPU played to termination"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--games", type=int, default=1 << 24, help="games per GPU per step (BASELINE config[1]: up to 16M)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall target of the cpu_baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("2048nn_b200")
+    eng = pkg.engine
+    n = args.games
+    gid_base = rank * n  # ranks play disjoint games of the same seed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # synthetic start boards: fresh 2-tile boards (generate_init_tiles distribution), resident in HBM
+    start = eng.init_boards(n, 777, gid_base)
+    out = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda"),
+           torch.empty(n, dtype=torch.int32, device="cuda"))
+    for w in range(args.warmup):
+        eng.playout_fixed(n, 1000 + w, gid_base, start=start, out=out)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timed region: exactly K steps -------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    moves = torch.zeros((), dtype=torch.int64, device="cuda")
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        eng.playout_fixed(n, 2000 + k, gid_base, start=start, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # move counts of the timed steps (recomputed outside the timed region from the last step,
+    # plus an exact recount per seed would cost K more passes; moves/step is seed-stable to 1e-4)
+    step_moves = []
+    for k in range(args.steps):
+        eng.playout_fixed(n, 2000 + k, gid_base, start=start, out=out)
+        step_moves.append(int(out[2].sum().item()))
+    total_moves = float(sum(step_moves))
+
+    # ---- end to end through the host-buffer API: H2D of start boards + D2H of results ------
+    hp = eng.HostPlayout(n)
+    h_start = start.cpu().pin_memory()
+    hp(h_start, 3000, gid_base)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_moves = 0
+    for k in range(args.steps):
+        hf, hs, hm = hp(h_start, 4000 + k, gid_base)
+        e2e_moves += int(hm.sum().item())  # host read of the step's result
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    tmax = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([total_moves, float(e2e_moves)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = tmax.tolist()
+    total_moves, e2e_moves = tot.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    value = total_moves / (ms * 1e-3)
+    e2e_value = e2e_moves / (e2e_ms * 1e-3)
+    sm_count = pkg._lib.load_library().b2048_num_sms(pkg._lib.ctx())
+    # roofline of the dominant kernel (playout_fixed_kernel): SM instruction-issue bound, not
+    # HBM and not tensor.  achieved = algorithmic thread-instr/s on ONE GPU.
+    per_gpu_moves_per_s = value / world
+    issue_peak = sm_count * 4 * 32 * peaks["sm_max_mhz"] * 1e6  # thread-instr/s at max SM clock
+    achieved = per_gpu_moves_per_s * INSTR_PER_MOVE
+    hbm_bytes = 24.0 * n * args.steps  # 8 B start + 16 B results per game
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(n), "games_per_gpu": n, "moves_per_step_per_gpu": step_moves[0],
+                   "order": "LUDR", "l2": "inputs+outputs (24 B/game = %d MB) larger than L2" % (24 * n >> 20),
+                   "parallelism": f"games sharded over {world} GPU(s), no data-path collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "sm_issue", "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
+                     "frac": achieved / issue_peak, "traffic": None,
+                     "note": "algorithmic 250 thread-instr/move x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); "
+                             "the kernel is integer-issue bound, HBM sees only %.1f GB/s of %.0f"
+                             % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
+                                peaks["hbm_gbs"])},
+    }
+    cores = os.cpu_count() or 1
+    if world == 1:
+        v, sample = cpu_port_rate(args.cpu_seconds, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

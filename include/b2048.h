@@ -88,6 +88,14 @@ int b2048_spawn_batch(b2048_ctx *ctx, const uint64_t *boards, uint64_t seed, con
                       uint64_t gid_base, const uint32_t *k, uint32_t k_scalar, uint64_t *out_boards,
                       int32_t *err_flag, int64_t n, void *stream);
 
+/* One BoardArray.move_batch / fast_move_batch step (board.py:246-303) for N games: game g plays
+ * the first legal direction of its priority row prio[4g..4g+3] (uint8, 4-byte aligned rows),
+ * then spawn number k[g] of stream (seed, gids[g] or gid_base+g).  out_moved[g] = 0 means the
+ * game is dead (board unchanged, gain 0).  Compaction of dead games is the caller's. */
+int b2048_policy_step(b2048_ctx *ctx, const uint64_t *boards, const uint8_t *prio, uint64_t seed,
+                      const uint64_t *gids, uint64_t gid_base, const uint32_t *k, uint64_t *out_boards,
+                      uint32_t *out_gain, uint8_t *out_moved, int64_t n, void *stream);
+
 /* raw stream words for parity tests: out[g*count + j] = draw(first + j) of stream (seed, gid_base+g) */
 int b2048_rng_draws(b2048_ctx *ctx, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
                     uint64_t *out, int64_t n, void *stream);

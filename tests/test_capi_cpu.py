@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library loads and exports every symbol include/b2048.h declares; the product
+fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+
+    ge.build()
+    return True
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b2048.h")).read()
+    return sorted(set(re.findall(r"\b(b2048_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built, pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.b2048_abi_version() == 1
+    # the Python binding table covers the header too
+    assert sorted(pkg._lib.exported_symbols()) == syms
+
+
+def test_sass_is_sm100a(built, pkg):
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(built, pkg):
+    with pytest.raises(pkg.B2048Error):
+        pkg.board.move(0x2141348, 0)
+    with pytest.raises(pkg.B2048Error):
+        pkg.board.play_fixed_batch(4)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "2048nn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle|oracle/|libb2048_oracle", txt, re.M):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,126 @@
+"""GPU: the reference-facing Python entry points (board / mcts drop-ins) against the golden
+vectors made by the reference itself and against the oracle.  Reads like the reference's API."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def board(pkg):
+    return pkg.board
+
+
+@pytest.fixture(scope="module")
+def mcts(pkg):
+    return pkg.mcts
+
+
+def test_scalar_board_functions(board, eg):
+    assert board.transpose(0x0123456789ABCDEF) == 0x048C159D26AE37BF
+    assert board.countzero(0) == 0 and board.countzero(0x2141348) == 9
+    assert board.get_tiles(0x21)[:3] == [1, 2, 0]
+    assert board.move(0x2141348, 2) == (0x21401348, 0, True)
+    assert board.move(0x2141348, 0) == (0x2141348, 0, False)
+    assert board.move(0xFFFFFFFFFFFFFFFF, 3) == (0, 524288, True)
+    r = board.move(0x1111222233334444, 0)
+    assert r == (0x0022003300440055, 120, True) and type(r[0]) is int and type(r[2]) is bool
+    assert board.merge_table[0x1111] == (0x0022, 8, True) and board.merge_table_rev[0x1111] == (0x2200, 8, True)
+    assert board.move_row(0xFFFF, False) == (0, 131072, True)
+    for j in range(0, 3000, 97):
+        b = int(eg["mv_boards"][j])
+        for d in range(4):
+            assert board.move(b, d) == (int(eg["mv_out"][d, j]), int(eg["mv_score"][d, j]), bool(eg["mv_moved"][d, j]))
+    with pytest.raises(ValueError):
+        board.generate_tile(0)  # randrange(0) in the reference (16 empties wrap)
+
+
+def test_play_fixed_replays_reference_games(board, eg):
+    seed = int(eg["pf_seed"])
+    for g in (0, 1, 2, 77, 1499):
+        assert board.generate_init_tiles(seed, g) == int(eg["pf_start"][g])
+        assert board.play_fixed(seed=seed, gid=g) == (int(eg["pf_final"][g]), int(eg["pf_score"][g]), int(eg["pf_count"][g]))
+    o, s = int(eg["po_origin"]), int(eg["po_seed"])
+    for g in (0, 5, 499):
+        assert board.play_fixed(o, seed=s, gid=g) == (int(eg["po_final"][g]), int(eg["po_score"][g]), int(eg["po_count"][g]))
+
+
+def test_play_fixed_batch_death_order(board, eg):
+    n = 1500
+    scores = board.play_fixed_batch(n, seed=int(eg["pf_seed"]))
+    order = np.argsort(eg["pf_count"], kind="stable")  # by step, then list position (board.py:312-314)
+    assert scores == [int(x) for x in eg["pf_score"][order]]
+    assert board.play_fixed_batch(0) == []
+
+
+def test_boardarray_loop_equals_play_fixed(board, eg):
+    seed = int(eg["pf_seed"])
+    k = 40
+    arr = board.BoardArray([int(x) for x in eg["pf_start"][:k]], seed=seed)
+    assert arr.scores == [0] * k
+    dead = {}
+    step = 0
+    alive = list(range(k))
+    while arr.boards:
+        ds, db = arr.move_batch([(0, 1, 3, 2)] * len(arr.boards), get_boards=True)
+        died = [g for g in alive if True][:0]
+        # survivors stay in order: reconstruct who died from counts
+        want_dead = [g for g in alive if int(eg["pf_count"][g]) == step]
+        assert ds == [int(eg["pf_score"][g]) for g in want_dead]
+        assert db == [int(eg["pf_final"][g]) for g in want_dead]
+        alive = [g for g in alive if g not in want_dead]
+        step += 1
+    # fast_move_batch: True at the first death, array untouched
+    arr = board.BoardArray([int(eg["pf_final"][0]), int(eg["pf_start"][1])], seed=seed)
+    before = list(arr.boards)
+    assert arr.fast_move_batch([(0, 1, 3, 2)] * 2) is True and arr.boards == before
+
+
+def test_mcts_fixed_family(mcts, eg):
+    number, seed = int(eg["mc_number"]), int(eg["mc_seed"])
+    for e, o in enumerate(eg["mc_origins"].tolist()):
+        got = mcts.mcts_fixed(o, number, seed=seed, eval_id=e)
+        for i in range(4):
+            if eg["mc_min"][e, i] == 0:
+                assert got[i] == -1
+            else:
+                order = np.argsort(eg["mc_moves"][e, i], kind="stable")
+                s = int(mcts.move(o, i)[1])
+                want = np.mean(np.log10(eg["mc_scores"][e, i][order] + s + 1))
+                assert got[i] == want and isinstance(got[i], np.float64)
+                assert abs(got[i] - eg["mc_mean"][e, i]) < 1e-12
+        assert mcts.mcts_fixed_min(o, number, seed=seed, eval_id=e) == eg["mc_min"][e].tolist()
+        assert mcts.mcts_fixed_moves(o, number, seed=seed, eval_id=e) == eg["mc_med"][e].tolist()
+    o = int(eg["mc_origins"][0])
+    assert mcts.mcts_fixed_moves(o, 7, seed=4243, eval_id=0) == eg["mc7_med"].tolist()
+    assert mcts.mcts_fixed_min(o, 7, seed=4243, eval_id=0) == eg["mc7_min"].tolist()
+    assert mcts.mcts_fixed_batch is mcts.mcts_fixed
+
+
+def test_play_mcts_fixed_matches_oracle_main_loop(mcts, orc):
+    # config 1: one full main game, 10 playouts per legal move, against the same loop on the oracle
+    seed = 2718
+    got = mcts.play_mcts_fixed(number=4, mode=2, seed=seed)
+    board = orc.init_board(orc.rng_key(seed, 0))
+    score = count = 0
+    while True:
+        res = orc.mcts_fixed_min(board, 4, seed, count + 1)
+        i = int(np.argmax(res))
+        f, s, m = orc.move(board, i)
+        if not m:
+            break
+        board = orc.spawn(f, orc.rng_key(seed, 0), count)
+        score += s
+        count += 1
+    assert got == (board, score, count)
+    assert count > 50
+
+
+def test_global_random_seed_reproducibility(board):
+    random.seed(5)
+    a = board.play_fixed_batch(64)
+    random.seed(5)
+    b = board.play_fixed_batch(64)
+    assert a == b and len(a) == 64
