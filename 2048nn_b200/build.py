@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "lib2048nn_b200.so")
 SOURCES = ["b2048_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
 ]
 
 

@@ -7,6 +7,7 @@
 
 #include "../../include/b2048.h"
 #include "engine_kernels.cuh"
+#include "playout_nn.cuh"
 
 using namespace b2048;
 
@@ -79,6 +80,9 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     if (mism) return fail_msg("b2048_create: row-table invariants violated");
     CK(cudaFuncSetAttribute(playout_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    CK(cudaFuncSetAttribute(convnet_fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            CN_FP32_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(playout_nn_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_FP32_SMEM_BYTES));
     *out = c;
     return 0;
 }
@@ -189,6 +193,7 @@ extern "C" int b2048_policy_step(b2048_ctx *c, const uint64_t *boards, const uin
     return 0;
 }
 
+static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st);
 static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     p.tb = tables_of(c);
     p.err_flag = c->err_flag;
@@ -233,13 +238,7 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
         return fail_msg("b2048_mcts_fixed: bad line range");
     if (!out_legal || !out_rscore) return fail_msg("b2048_mcts_fixed: out_legal and out_rscore are required");
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->rboard_cap < G * 4) {  // scratch for the boards after the root move; grows rarely
-        CK(cudaStreamSynchronize(st));
-        cudaFree(c->rboard);
-        int64_t cap = G * 4 < 4096 ? 4096 : G * 4;
-        CK(cudaMalloc(&c->rboard, cap * sizeof(uint64_t)));
-        c->rboard_cap = cap;
-    }
+    if (int rc = ensure_rboard(c, G, st)) return rc;
     root_moves_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
                                                                        out_legal, out_rscore, (u64 *)c->rboard);
     CK(cudaGetLastError());
@@ -264,4 +263,109 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
     p.out_count = out_count;
     p.out_minmov = out_minmov;
     return launch_playout(c, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Policy network (network.py:43-87) and NN-policy playouts (mcts_nn.py, eval_nn.py)
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t b2048_convnet_blob_bytes(int precision) {
+    if (precision == B2048_PREC_FP32) return (int64_t)CN_FP32_FLOATS * 4;
+    return -1;
+}
+
+static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st) {
+    if (c->rboard_cap < G * 4) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c->rboard);
+        int64_t cap = G * 4 < 4096 ? 4096 : G * 4;
+        CK(cudaMalloc(&c->rboard, cap * sizeof(uint64_t)));
+        c->rboard_cap = cap;
+    }
+    return 0;
+}
+
+extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *blob, const uint64_t *boards,
+                                     float *out_logp, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    if (!blob || !boards || !out_logp) return fail_msg("b2048_convnet_forward: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == B2048_PREC_FP32) {
+        int grid = grid_for(n, CN_BOARDS_PER_CTA, c->num_sms * 2);
+        convnet_fp32_forward_kernel<<<grid, 512, CN_FP32_SMEM_BYTES, st>>>((const float *)blob, (const u64 *)boards,
+                                                                           out_logp, (long)n);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    return fail_msg("b2048_convnet_forward: unknown precision");
+}
+
+static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t st) {
+    p.tb = tables_of(c);
+    p.err_flag = c->err_flag;
+    unsigned slot = (c->next_counter++) % N_COUNTERS;
+    p.counter = c->counters + slot;
+    CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
+    if (precision == B2048_PREC_FP32) {
+        int grid = grid_for(p.n, CN_BOARDS_PER_CTA, c->num_sms * 2);
+        playout_nn_fp32_kernel<<<grid, 512, CN_FP32_SMEM_BYTES, st>>>(p);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    return fail_msg("b2048 NN playout: unknown precision");
+}
+
+extern "C" int b2048_playout_nn(b2048_ctx *c, int precision, const void *blob, const uint64_t *start, uint64_t seed,
+                                uint64_t gid_base, uint32_t spawn0, int group_size, int32_t *group_min,
+                                uint64_t *out_final, uint32_t *out_score, uint32_t *out_moves,
+                                uint64_t *move_counter, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    if (!blob) return fail_msg("b2048_playout_nn: blob is NULL");
+    NNPlayParams p;
+    memset(&p, 0, sizeof p);
+    p.blob = (const float *)blob;
+    p.n = (long)n;
+    p.start = (const u64 *)start;
+    p.seed = seed;
+    p.gid_base = gid_base;
+    p.spawn0 = spawn0;
+    p.group_size = group_size;
+    p.group_min = group_min;
+    p.out_final = (u64 *)out_final;
+    p.out_score = out_score;
+    p.out_moves = out_moves;
+    p.move_counter = (unsigned long long *)move_counter;
+    return launch_nn(c, precision, p, (cudaStream_t)stream);
+}
+
+extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, const uint64_t *origins, int64_t G,
+                             int number, int line_begin, int line_end, uint64_t seed, uint64_t eval_id_base,
+                             uint8_t *out_legal, uint32_t *out_rscore, uint32_t *out_lmoves, int32_t *out_minmov,
+                             uint64_t *move_counter, void *stream) {
+    if (G <= 0) return 0;
+    if (number <= 0 || line_begin < 0 || line_end > number || line_begin > line_end)
+        return fail_msg("b2048_mcts_nn: bad line range");
+    if (!blob || !out_legal || !out_rscore || !out_minmov) return fail_msg("b2048_mcts_nn: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_rboard(c, G, st)) return rc;
+    root_moves_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
+                                                                       out_legal, out_rscore, (u64 *)c->rboard);
+    CK(cudaGetLastError());
+    if (line_begin == line_end) return 0;
+    NNPlayParams p;
+    memset(&p, 0, sizeof p);
+    p.blob = (const float *)blob;
+    p.root_mode = 1;
+    p.rboard = (const u64 *)c->rboard;
+    p.rlegal = out_legal;
+    p.number = number;
+    p.line_begin = line_begin;
+    p.line_count = line_end - line_begin;
+    p.n = (long)G * 4 * p.line_count;
+    p.seed = seed;
+    p.gid_base = eval_id_base * 4ULL;
+    p.spawn0 = 1;
+    p.group_min = out_minmov;
+    p.out_moves = out_lmoves;
+    p.move_counter = (unsigned long long *)move_counter;
+    return launch_nn(c, precision, p, st);
 }

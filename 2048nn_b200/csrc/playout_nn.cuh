@@ -1,0 +1,168 @@
+// playout_nn.cuh -- K4: persistent NN-policy playout kernels (mcts_nn.py:4-43 mcts_nn,
+// mcts_nn.py:46-94 play_nn, eval_nn.py:4-95 eval_nn / eval_nn_min).
+//
+// A CTA owns a small set of game slots and loops {refill empty slots from the global work
+// counter; one policy forward for all its boards; per game: first legal move in descending
+// logit order (mcts_nn.py:36-37 argsort + board.py:264-269), spawn}, entirely on the device:
+// no host round trip per move.  Work items are "lines" (root-search) or whole games.
+//
+// Min-move reduction with early stop (mcts_nn.py:37-39, eval_nn.py:91-93): every game belongs to
+// a group; a group's result is min_j L_j.  A game stops as soon as its move count reaches the
+// group's current minimum, because it can no longer lower it -- the minimum itself is
+// independent of scheduling, so results are deterministic.
+#pragma once
+#include "convnet_fp32.cuh"
+#include "engine.cuh"
+
+namespace b2048 {
+
+struct NNPlayParams {
+    Tables tb;
+    const float *blob;  // folded fp32 weights (convnet_fp32.cuh layout)
+    long n;             // work items
+    // whole-game mode
+    const u64 *start;  // start boards (NULL / 0 entry -> fresh board)
+    // root mode
+    int root_mode;
+    const u64 *rboard;      // [G*4] boards after the root move
+    const uint8_t *rlegal;  // [G*4]
+    int number, line_begin, line_count;
+    u64 seed, gid_base;
+    u32 spawn0;
+    // grouping for the min reduction: group = item / group_size (whole-game mode) or root index
+    int group_size;      // 0 = no grouping (play every game to the end)
+    int *group_min;      // [groups], caller-initialised to INT32_MAX
+    // per-item outputs (may be NULL)
+    u64 *out_final;
+    u32 *out_score;
+    u32 *out_moves;
+    unsigned long long *counter;
+    unsigned long long *move_counter;  // total accepted moves (for throughput accounting), may be NULL
+    int *err_flag;
+};
+
+struct GameSlot {
+    u64 board, key;
+    u32 score, count;
+    long slot;   // output index
+    int group;   // -1 = none
+    int live;
+};
+
+// fetch + initialise one work item into `g`; returns false when the queue is empty.
+__device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
+    for (;;) {
+        long item = (long)atomicAdd(p.counter, 1ULL);
+        if (item >= p.n) return false;
+        g.score = 0;
+        g.count = 0;
+        g.group = -1;
+        if (p.root_mode) {
+            long r = item / p.line_count;
+            int j = p.line_begin + (int)(item - r * p.line_count);
+            g.slot = r * p.number + j;
+            if (!p.rlegal[r]) {
+                if (p.out_final) p.out_final[g.slot] = 0;
+                if (p.out_score) p.out_score[g.slot] = 0;
+                if (p.out_moves) p.out_moves[g.slot] = 0;
+                continue;
+            }
+            g.key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
+            u64 rb = p.rboard[r];
+            if (countzero(rb) == 0) {
+                *p.err_flag = 1;
+                continue;
+            }
+            u32 four;
+            g.board = spawn_tile(rb, rng_draw(g.key, B2048_INIT_DRAWS), four);  // mcts_nn.py:22
+            if (p.group_min) g.group = (int)r;
+        } else {
+            g.slot = item;
+            g.key = rng_key(p.seed, p.gid_base + (u64)item);
+            u64 s0 = p.start ? p.start[item] : 0ULL;
+            g.board = s0 ? s0 : init_board(g.key);
+            if (p.group_min && p.group_size > 0) g.group = (int)(item / p.group_size);
+        }
+        g.live = 1;
+        return true;
+    }
+}
+
+__device__ __forceinline__ void nn_finish(const NNPlayParams &p, GameSlot &g) {
+    if (p.out_final) p.out_final[g.slot] = g.board;
+    if (p.out_score) p.out_score[g.slot] = g.score;
+    if (p.out_moves) p.out_moves[g.slot] = g.count;
+    if (g.group >= 0) atomicMin(p.group_min + g.group, (int)g.count);
+    g.live = 0;
+}
+
+// One policy move for a live game given its 4 logits: directions in descending logit order
+// (stable: ties go to the lower direction index), first legal one is played.
+__device__ __forceinline__ void nn_move(const NNPlayParams &p, GameSlot &g, const float *z, u32 &moves_done) {
+    // early stop: cannot lower the group's minimum any more
+    if (g.group >= 0 && (int)g.count >= *((volatile int *)(p.group_min + g.group))) {
+        nn_finish(p, g);
+        return;
+    }
+    int order[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int a = 1; a < 4; a++)  // insertion sort, descending, stable
+#pragma unroll
+        for (int c = a; c > 0; c--)
+            if (z[order[c]] > z[order[c - 1]]) {
+                int t = order[c];
+                order[c] = order[c - 1];
+                order[c - 1] = t;
+            }
+    bool moved = false;
+#pragma unroll 1
+    for (int a = 0; a < 4 && !moved; a++) {
+        u32 s;
+        u64 f = move_exact(g.board, order[a], p.tb, s);
+        if (f != g.board) {
+            if (countzero(f) == 0) {
+                *p.err_flag = 1;
+                nn_finish(p, g);
+                return;
+            }
+            u32 four;
+            g.board = spawn_tile(f, rng_draw(g.key, B2048_INIT_DRAWS + p.spawn0 + g.count), four);
+            g.score += s;
+            g.count++;
+            moves_done++;
+            moved = true;
+        }
+    }
+    if (!moved) nn_finish(p, g);
+}
+
+// Exact-mode kernel: 8 game slots per CTA, fp32 CUDA-core forward.
+__global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float *act0 = smem, *act1 = smem + 8 * 64 * 16, *s_head = act1 + 8 * 64 * 16, *s_logits = s_head + 8 * 64;
+    u64 *s_boards = reinterpret_cast<u64 *>(s_logits + 32);
+    __shared__ int s_live;
+    GameSlot g;
+    g.live = 0;
+    g.board = 0;
+    u32 moves_done = 0;
+    bool queue_empty = false;
+    const int t = threadIdx.x;
+    for (;;) {
+        if (t == 0) s_live = 0;
+        __syncthreads();
+        if (t < CN_BOARDS_PER_CTA) {
+            if (!g.live && !queue_empty) queue_empty = !nn_fetch(p, g);
+            s_boards[t] = g.live ? g.board : 0ULL;
+            if (g.live) atomicOr(&s_live, 1);
+        }
+        __syncthreads();
+        if (!s_live) break;
+        convnet_fp32_cta(p.blob, s_boards, CN_BOARDS_PER_CTA, act0, act1, s_head, s_logits);
+        if (t < CN_BOARDS_PER_CTA && g.live) nn_move(p, g, s_logits + 4 * t, moves_done);
+        __syncthreads();
+    }
+    if (t < CN_BOARDS_PER_CTA && p.move_counter && moves_done) atomicAdd(p.move_counter, (unsigned long long)moves_done);
+}
+
+}  // namespace b2048

@@ -140,6 +140,43 @@ def mcts_fixed_lines(origins, number, seed, eval_id_base=0, line_begin=0, line_e
     return r
 
 
+PRECISIONS = {"fp32": 0, "fp16": 1}
+
+
+def playout_nn(blob, precision, n, seed, gid_base=0, start=None, spawn0=0, group_size=0, device="cuda", want_final=True):
+    """K4: n NN-policy games in one persistent kernel (eval_nn.py:4-95, mcts_nn.py:46-94).
+    -> dict(final i64[n], score i32[n], moves i32[n], group_min i32[groups] or None, total_moves i64[1])"""
+    L.require_cuda()
+    d = torch.device(device) if start is None else _dev(start)
+    r = dict(final=torch.empty(n, dtype=torch.int64, device=d) if want_final else None,
+             score=torch.empty(n, dtype=torch.int32, device=d), moves=torch.empty(n, dtype=torch.int32, device=d),
+             total_moves=torch.zeros(1, dtype=torch.int64, device=d), group_min=None)
+    if group_size > 0:
+        r["group_min"] = torch.full(((n + group_size - 1) // group_size,), 2**31 - 1, dtype=torch.int32, device=d)
+    L.check(L.load_library().b2048_playout_nn(L.ctx(d), PRECISIONS[precision], L.ptr(blob), L.ptr(start), seed, gid_base,
+                                              spawn0, group_size, L.ptr(r["group_min"]), L.ptr(r["final"]), L.ptr(r["score"]),
+                                              L.ptr(r["moves"]), L.ptr(r["total_moves"]), n, L.stream_ptr(d)))
+    return r
+
+
+def mcts_nn_lines(blob, precision, origins, number, seed, eval_id_base=0, line_begin=0, line_end=None, per_line=False):
+    """mcts_nn.py:4-43 for G origins: legal u8[G,4], rscore i32[G,4], minmov i32[G,4] (INT32_MAX
+    where no line was played), lmoves i32[G,4,number] when per_line, total_moves i64[1]."""
+    d = _dev(origins)
+    G = origins.numel()
+    line_end = number if line_end is None else line_end
+    r = dict(legal=torch.empty((G, 4), dtype=torch.uint8, device=d), rscore=torch.empty((G, 4), dtype=torch.int32, device=d),
+             minmov=torch.full((G, 4), 2**31 - 1, dtype=torch.int32, device=d),
+             total_moves=torch.zeros(1, dtype=torch.int64, device=d))
+    if per_line:
+        r["lmoves"] = torch.zeros((G, 4, number), dtype=torch.int32, device=d)
+    L.check(L.load_library().b2048_mcts_nn(L.ctx(d), PRECISIONS[precision], L.ptr(blob), L.ptr(origins), G, number, line_begin,
+                                           line_end, seed, eval_id_base, L.ptr(r["legal"]), L.ptr(r["rscore"]),
+                                           L.ptr(r.get("lmoves")), L.ptr(r["minmov"]), L.ptr(r["total_moves"]),
+                                           L.stream_ptr(d)))
+    return r
+
+
 class HostPlayout:
     """Host-buffer front end of K2 for large batches: pinned host start boards in, pinned host
     (final, score, moves) out, with the H2D / D2H copies enqueued on the same stream as the

@@ -1,0 +1,103 @@
+"""Drop-in for the reference's `network.ConvNet` (network.py:43-87), c64b3 on the B200.
+
+`ConvNet(channels=64, blocks=3)` has the reference's module tree, so `load_state_dict` accepts
+the reference checkpoints unchanged (same 50 keys) and `parameters()`
+counts 231,820.  In eval mode `forward` takes the reference's `(N,16,4,4)` one-hot float input
+and returns `(N,4)` log-probabilities computed by the CUDA kernels (b2048_convnet_forward);
+`forward_boards` takes packed uint64 boards directly (8 B instead of 1,024 B per board).
+
+precision: "fp32" = exact mode (CUDA-core FMA, |dlogp| ~1e-5 vs PyTorch);
+           "fp16" = tcgen05 tensor-core mode (fp16 operands, fp32 accumulation).
+Training (autograd through forward) is outside this path and raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import convnet as _cn
+
+PRECISIONS = {"fp32": 0, "fp16": 1}
+
+
+class ConvNet(nn.Module):
+    def __init__(self, channels=16, blocks=5, out_c=4, precision="fp32"):
+        super().__init__()
+        self.relu = nn.ReLU(inplace=True)
+        self.in_block = nn.Sequential(nn.Conv2d(16, channels, 3, padding=1, bias=False), nn.BatchNorm2d(channels),
+                                      nn.ReLU(inplace=True))
+        self.blocks = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(channels, channels, 3, padding=1, bias=False), nn.BatchNorm2d(channels),
+                          nn.ReLU(inplace=True), nn.Conv2d(channels, channels, 3, padding=1, bias=False),
+                          nn.BatchNorm2d(channels)) for _ in range(blocks)])
+        self.out_block = nn.Sequential(nn.Conv2d(channels, out_c, 1, padding=0, bias=False), nn.BatchNorm2d(out_c),
+                                       nn.ReLU(inplace=True))
+        self.out_size = out_c * 16
+        self.policy = nn.Linear(self.out_size, 4)
+        self.soft = nn.LogSoftmax(dim=1)
+        self._shape = (channels, blocks, out_c)
+        self.precision = precision
+        self._blob = None
+        self._blob_key = None
+
+    # ---- weight image management ------------------------------------------------------------
+    def _state_version(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def blob(self, precision=None):
+        """Folded-weight device image for the CUDA kernels (rebuilt when parameters change)."""
+        precision = precision or self.precision
+        if self._shape != (64, 3, 4):
+            raise NotImplementedError("the B200 kernels implement c64b3 = ConvNet(channels=64, blocks=3)")
+        L.require_cuda()
+        key = (precision, self._state_version())
+        if self._blob_key != key:
+            folded = _cn.fold_state_dict(self.state_dict())
+            if precision == "fp32":
+                b = _cn.pack_fp32(folded)
+            else:
+                b = _cn.pack_tc(folded)
+            dev = next(self.parameters()).device
+            dev = dev if dev.type == "cuda" else torch.device("cuda")
+            self._blob, self._blob_key = b.to(dev), key
+        return self._blob
+
+    # ---- inference -----------------------------------------------------------------------------
+    def forward_boards(self, boards, precision=None):
+        """boards: int64 device tensor (uint64 bit patterns) -> (N,4) float32 log-probs."""
+        precision = precision or self.precision
+        blob = self.blob(precision)
+        boards = boards.contiguous()
+        n = boards.numel()
+        out = torch.empty((n, 4), dtype=torch.float32, device=boards.device)
+        L.check(L.load_library().b2048_convnet_forward(L.ctx(boards.device), PRECISIONS[precision], L.ptr(blob),
+                                                       L.ptr(boards), L.ptr(out), n, L.stream_ptr(boards.device)))
+        return out
+
+    def forward(self, x):
+        """network.py:78-87.  x: (N,16,4,4) one-hot float tensor as built by mcts_nn.py:25-35."""
+        if self.training:
+            raise NotImplementedError("2048nn_b200.ConvNet is inference-only: call model.eval() as the reference's "
+                                      "playout callers do (selfplay.py:91-92, eval_nn.py:26)")
+        L.require_cuda()
+        x = x.reshape(-1, 16, 16)
+        # the kernel consumes packed boards: recover the exponent of each cell from the one-hot planes
+        expo = x.argmax(dim=1).to(torch.int64)  # (N,16) position-major
+        shifts = torch.arange(16, device=x.device, dtype=torch.int64) * 4
+        boards = (expo << shifts).sum(dim=1)  # nibble 15 << 60 wraps into the sign bit: same bit pattern
+        return self.forward_boards(boards.to("cuda"))
+
+
+def blob_for(model, precision=None):
+    """Weight image for any module carrying the reference's c64b3 state_dict (our ConvNet or the
+    reference's own torch ConvNet); cached on the module."""
+    if isinstance(model, ConvNet):
+        return model.blob(precision), (precision or model.precision)
+    precision = precision or getattr(model, "precision", "fp32")
+    cache = model.__dict__.setdefault("_b2048_blobs", {})
+    key = (precision, tuple((p.data_ptr(), p._version) for p in model.state_dict().values()))
+    if cache.get("key") != key:
+        folded = _cn.fold_state_dict(model.state_dict())
+        b = _cn.pack_fp32(folded) if precision == "fp32" else _cn.pack_tc(folded)
+        L.require_cuda()
+        cache["key"], cache["blob"] = key, b.cuda()
+    return cache["blob"], precision

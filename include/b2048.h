@@ -129,6 +129,49 @@ int b2048_mcts_fixed(b2048_ctx *ctx, const uint64_t *origins, int64_t G, int num
                      uint32_t *out_rscore, uint32_t *out_lscore, uint32_t *out_lmoves, int64_t *out_logsum,
                      int32_t *out_count, int32_t *out_minmov, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Policy network c64b3 = ConvNet(channels=64, blocks=3) (network.py:43-87) and NN-policy
+ * playouts.  `blob` is the folded-weight image made by 2048nn_b200/convnet.py from a reference
+ * state_dict (BatchNorm folded in float64, eval mode, eps 1e-5).
+ *   B2048_PREC_FP32: CUDA-core fp32 forward, bit-close to PyTorch fp32 (exact mode)
+ *   B2048_PREC_FP16_TC: tcgen05 tensor-core forward, fp16 operands, fp32 accumulation
+ * ------------------------------------------------------------------------------------------ */
+#define B2048_PREC_FP32 0
+#define B2048_PREC_FP16_TC 1
+
+/* size in bytes of the weight blob for a precision (-1: unsupported) */
+int64_t b2048_convnet_blob_bytes(int precision);
+
+/* ConvNet.forward fused with the inline one-hot encoder (mcts_nn.py:25-35, network.py:78-87):
+ * boards u64[N] -> log-probabilities f32[N*4] (order Left, Up, Right, Down). */
+int b2048_convnet_forward(b2048_ctx *ctx, int precision, const void *blob, const uint64_t *boards,
+                          float *out_logp, int64_t n, void *stream);
+
+/* N policy games inside one persistent kernel (eval_nn.py:4-58 eval_nn, :61-95 eval_nn_min,
+ * mcts_nn.py:46-94 play_nn): each move is the first legal direction in descending order of the
+ * network's outputs (mcts_nn.py:36-37 + board.py:264-269; ties -> lower index).
+ *   start       N start boards or NULL (fresh); 0 entry -> fresh board
+ *   group_size  > 0 with group_min != NULL: games [k*group_size, (k+1)*group_size) form a group
+ *               whose min accepted-move count is accumulated (atomic min) into group_min[k]
+ *               (caller initialises to INT32_MAX); games stop early once they cannot lower it
+ *               (eval_nn_min's first-death semantics).  Otherwise every game runs to its end.
+ *   move_counter  optional u64[1], += accepted moves played (throughput accounting)
+ * outputs per game (may be NULL): final board, score, accepted moves. */
+int b2048_playout_nn(b2048_ctx *ctx, int precision, const void *blob, const uint64_t *start, uint64_t seed,
+                     uint64_t gid_base, uint32_t spawn0, int group_size, int32_t *group_min, uint64_t *out_final,
+                     uint32_t *out_score, uint32_t *out_moves, uint64_t *move_counter, int64_t n, void *stream);
+
+/* mcts_nn (mcts_nn.py:4-43) for G origins: lines [line_begin,line_end) of `number` per root move.
+ *   out_legal u8[G*4], out_rscore u32[G*4] (root merge score; the reference discards it),
+ *   out_lmoves u32[G*4*number] per-line moves at stop (may be NULL; lines stopped early report
+ *   the count at which they stopped), out_minmov i32[G*4] ACCUMULATED min_j L_j (caller
+ *   initialises to INT32_MAX).  mcts_nn's value is 1 + min (0 when illegal).  Ranks allreduce
+ *   out_minmov with MIN. */
+int b2048_mcts_nn(b2048_ctx *ctx, int precision, const void *blob, const uint64_t *origins, int64_t G, int number,
+                  int line_begin, int line_end, uint64_t seed, uint64_t eval_id_base, uint8_t *out_legal,
+                  uint32_t *out_rscore, uint32_t *out_lmoves, int32_t *out_minmov, uint64_t *move_counter,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif
