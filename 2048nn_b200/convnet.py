@@ -49,3 +49,47 @@ def pack_fp32(folded):
         parts.append(b)
     parts += [folded["head_w"].reshape(-1), folded["head_b"], folded["fc_w"].reshape(-1), folded["fc_b"]]
     return torch.from_numpy(np.concatenate(parts).astype(np.float32))
+
+
+# ---- tensor-core image (csrc/convnet_tc.cuh) -------------------------------------------------------
+TC_CHUNK_ROWS, TC_ROW_BYTES = 192, 128
+
+
+def _swizzle_rows(rows_u16):
+    """rows_u16: (R, 64) uint16 (fp16 bits), R multiple of 8 -> SWIZZLE_128B image: 16-byte chunk c of
+    row r is stored at chunk position c ^ (r % 8)."""
+    R = rows_u16.shape[0]
+    chunks = rows_u16.reshape(R, 8, 8)
+    out = np.empty_like(chunks)
+    r = np.arange(R)
+    for c in range(8):
+        out[r, c ^ (r & 7)] = chunks[r, c]
+    return out.reshape(R, 64)
+
+
+def pack_tc(folded):
+    """fp16 tensor-core blob: 21 chunks (layer l, ky) of 192 rows [kx=2 | kx=1 | kx=0] x 64 co, each row
+    64 ci fp16 (K-major, pre-swizzled); L0 rows are [W_hi(16 ci) | W_lo(16 ci) | 0]; then the fp32 tail
+    bias[7][64], w7[4][64], b7[4], fcw[4][64], fcb[4]."""
+    chunks = []
+    for l, w in enumerate(folded["conv_w"]):  # (64 co, cin, 3, 3) float64
+        for ky in range(3):
+            rows = np.zeros((TC_CHUNK_ROWS, 64), np.float32)
+            rows_lo = None
+            for blk, kx in enumerate((2, 1, 0)):  # dx = +1, 0, -1  ->  output column x = s-1, s, s+1
+                wk = w[:, :, ky, kx]  # (co, ci)
+                if l == 0:
+                    hi = wk.astype(np.float16)
+                    lo = (wk - hi.astype(np.float64)).astype(np.float16)
+                    rows[blk * 64:(blk + 1) * 64, 0:16] = hi.astype(np.float32)
+                    rows[blk * 64:(blk + 1) * 64, 16:32] = lo.astype(np.float32)
+                else:
+                    rows[blk * 64:(blk + 1) * 64, :] = wk.astype(np.float32)
+            h = rows.astype(np.float16)
+            if not np.isfinite(h.astype(np.float32)).all():
+                raise ValueError("folded weights overflow fp16")
+            chunks.append(_swizzle_rows(h.view(np.uint16)).reshape(-1))
+    wbytes = np.concatenate(chunks).view(np.uint8)
+    tail = np.concatenate([np.stack(folded["conv_b"]).reshape(-1), folded["head_w"].reshape(-1), folded["head_b"],
+                           folded["fc_w"].reshape(-1), folded["fc_b"]]).astype(np.float32)
+    return torch.from_numpy(np.concatenate([wbytes, tail.view(np.uint8)]).copy())

@@ -8,6 +8,7 @@
 #include "../../include/b2048.h"
 #include "engine_kernels.cuh"
 #include "playout_nn.cuh"
+#include "convnet_tc.cuh"
 
 using namespace b2048;
 
@@ -82,6 +83,8 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CK(cudaFuncSetAttribute(convnet_fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             CN_FP32_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::convnet_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(playout_nn_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_FP32_SMEM_BYTES));
     *out = c;
     return 0;
@@ -270,6 +273,7 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t b2048_convnet_blob_bytes(int precision) {
     if (precision == B2048_PREC_FP32) return (int64_t)CN_FP32_FLOATS * 4;
+    if (precision == B2048_PREC_FP16_TC) return (int64_t)tc::BLOB_BYTES;
     return -1;
 }
 
@@ -296,7 +300,39 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
         CK(cudaGetLastError());
         return 0;
     }
+    if (precision == B2048_PREC_FP16_TC) {
+        tc::FwdParams p;
+        memset(&p, 0, sizeof p);
+        p.blob = (const uint8_t *)blob;
+        p.boards = (const unsigned long long *)boards;
+        p.out_logp = out_logp;
+        p.n = (long)n;
+        p.dbg_layer = -1;
+        int grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
+        tc::convnet_tc_forward_kernel<<<grid, 320, tc::SMEM_BYTES, st>>>(p);
+        CK(cudaGetLastError());
+        return 0;
+    }
     return fail_msg("b2048_convnet_forward: unknown precision");
+}
+
+/* Debug/bring-up entry of the tensor-core forward: pre-softmax logits and, when dbg != NULL, the
+ * fp32 post-activation output of conv layer `dbg_layer` (0..6) as [board][64 co][16 pos]. */
+extern "C" int b2048_convnet_tc_debug(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logits,
+                                      float *dbg, int dbg_layer, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    tc::FwdParams p;
+    memset(&p, 0, sizeof p);
+    p.blob = (const uint8_t *)blob;
+    p.boards = (const unsigned long long *)boards;
+    p.out_logits = out_logits;
+    p.n = (long)n;
+    p.dbg = dbg;
+    p.dbg_layer = dbg ? dbg_layer : -1;
+    int grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
+    tc::convnet_tc_forward_kernel<<<grid, 320, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t st) {

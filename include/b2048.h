@@ -147,6 +147,12 @@ int64_t b2048_convnet_blob_bytes(int precision);
 int b2048_convnet_forward(b2048_ctx *ctx, int precision, const void *blob, const uint64_t *boards,
                           float *out_logp, int64_t n, void *stream);
 
+/* Bring-up/diagnostic entry of the tensor-core forward: pre-softmax outputs f32[N*4] and, when
+ * dbg != NULL, the fp32 post-activation output of conv layer dbg_layer (0 = in_block, 1..6 = the
+ * block convs) as [board][64 channels][16 positions]. */
+int b2048_convnet_tc_debug(b2048_ctx *ctx, const void *blob, const uint64_t *boards, float *out_logits, float *dbg,
+                           int dbg_layer, int64_t n, void *stream);
+
 /* N policy games inside one persistent kernel (eval_nn.py:4-58 eval_nn, :61-95 eval_nn_min,
  * mcts_nn.py:46-94 play_nn): each move is the first legal direction in descending order of the
  * network's outputs (mcts_nn.py:36-37 + board.py:264-269; ties -> lower index).
