@@ -1,0 +1,91 @@
+"""Multi-GPU sharding of root evaluations: one process per GPU, torch.distributed over NCCL.
+
+Playouts are independent, so a root evaluation shards by LINES: rank r plays lines
+[begin_r, end_r) of every (origin, root move) with the same (seed, eval_id) keyed streams, and
+the ranks combine their partial statistics with ONE small allreduce:
+
+    mean-log (mcts.py:4-34)      logsum i64[G,4] fixed-point + count i32[G,4]   SUM
+    min-move (mcts.py:73-103,
+              mcts_nn.py:4-43)   minmov i32[G,4]                                MIN
+
+Because the streams are keyed by (seed, game id) and the fused sums are integers, the reduced
+statistics are bit-identical for every world size (tests/test_dist_cpu.py, test_engine_gpu.py).
+The reduction helpers take plain tensors, so the host logic is testable with gloo on CPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+LOGSUM_SCALE = float(2 ** 40)  # B2048_LOGSUM_FRAC_BITS
+INT32_MAX = 2 ** 31 - 1
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_lines(number, rank, world_size):
+    """Contiguous split of `number` lines over ranks: sizes differ by at most one."""
+    base, rem = divmod(int(number), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allreduce_root_stats(stats, group=None):
+    """In-place allreduce of a partial-statistics dict (keys present among logsum/count: SUM;
+    minmov: MIN).  No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    if "logsum" in stats and stats["logsum"] is not None:
+        packed = torch.stack([stats["logsum"], stats["count"].to(torch.int64)])  # one collective for both
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        stats["logsum"].copy_(packed[0])
+        stats["count"].copy_(packed[1].to(stats["count"].dtype))
+    if "minmov" in stats and stats["minmov"] is not None:
+        dist.all_reduce(stats["minmov"], op=dist.ReduceOp.MIN, group=group)
+    return stats
+
+
+def mean_log_from_stats(legal, logsum, count):
+    """mcts_fixed values from reduced statistics: mean log10 per root move, -1 where illegal."""
+    legal = legal.to(torch.bool)
+    mean = logsum.to(torch.float64) / LOGSUM_SCALE / count.clamp(min=1).to(torch.float64)
+    return torch.where(legal, mean, torch.full_like(mean, -1.0))
+
+
+def min_from_stats(legal, minmov, illegal_value=0):
+    """mcts_fixed_min / mcts_nn values: 1 + min_j L_j, `illegal_value` where the move is illegal."""
+    legal = legal.to(torch.bool)
+    return torch.where(legal, minmov.to(torch.int64) + 1, torch.full_like(minmov, illegal_value, dtype=torch.int64))
+
+
+# ---- sharded root evaluations on the GPU --------------------------------------------------------
+def mcts_fixed_sharded(origins, number, seed, eval_id_base=0, group=None):
+    """Fixed-order root search for G origins with the lines sharded over the process group.
+    Returns dict(legal, rscore, logsum, count, minmov, mean, min) -- identical on every rank."""
+    from . import engine
+
+    rank, ws = world()
+    b, e = shard_lines(number, rank, ws)
+    r = engine.mcts_fixed_lines(origins, number, seed, eval_id_base, b, e, per_line=False, fused=True)
+    allreduce_root_stats(r, group)
+    r["mean"] = mean_log_from_stats(r["legal"], r["logsum"], r["count"])
+    r["min"] = min_from_stats(r["legal"], r["minmov"])
+    return r
+
+
+def mcts_nn_sharded(blob, precision, origins, number, seed, eval_id_base=0, group=None):
+    """NN-policy root search (mcts_nn.py:4-43) with the lines sharded over the process group.
+    Early stopping uses each rank's local minimum; the allreduce(MIN) restores the global one."""
+    from . import engine
+
+    rank, ws = world()
+    b, e = shard_lines(number, rank, ws)
+    r = engine.mcts_nn_lines(blob, precision, origins, number, seed, eval_id_base, b, e)
+    allreduce_root_stats(r, group)
+    r["min"] = min_from_stats(r["legal"], r["minmov"])
+    if ws > 1:
+        dist.all_reduce(r["total_moves"], op=dist.ReduceOp.SUM, group=group)
+    return r

@@ -1,0 +1,112 @@
+"""Self-play record generation (fqjin/2048NN selfplay.py) for a BATCH of concurrent main games.
+
+`selfplay` / `selfplay_fixed` keep the reference's single-game signatures and npz format
+(selfplay.py:55-58,111-114: boards uint64[T], results float32[T,4], score).  `selfplay_batch`
+is the B200 shape of BASELINE config 4: G main games advance in lock-step; every main step is
+ONE persistent-kernel launch evaluating G x 4 x number playout lines (sharded over the process
+group's GPUs), one [G,4] allreduce, and a handful of tiny device ops to pick argmax, move and
+spawn.  The main boards stay on the device; the host reads one scalar per main step."""
+import os
+
+import numpy as np
+import torch
+
+from . import dist as _dist
+from . import engine
+from .board import _session_seed
+from .network import blob_for
+
+
+def _eval_ids(step, G):
+    # evaluation id of main game g at main step t: disjoint stream ranges per (t, g)
+    return (step + 1) * G
+
+
+def selfplay_batch(G, number=10, model=None, times=1, seed=None, precision=None, starts=None, max_steps=100000,
+                   group=None):
+    """Play G main games to the end.  model=None -> fixed-order playouts scored by
+    mcts_fixed_min averaged over `times` (selfplay.py:9-59); else NN-policy mcts_nn (selfplay.py:62-115).
+
+    Returns a list of G records dict(boards uint64[T], results float32[T,4], score int) and the
+    total number of playout moves (all ranks)."""
+    s = _session_seed(seed)
+    dev = torch.device("cuda")
+    boards = engine.init_boards(G, s, 0, device=dev) if starts is None else starts.to(dev).clone()
+    gids = torch.arange(G, dtype=torch.int64, device=dev)
+    alive = torch.ones(G, dtype=torch.bool, device=dev)
+    score = torch.zeros(G, dtype=torch.int64, device=dev)
+    kmain = torch.zeros(G, dtype=torch.int32, device=dev)
+    hist_b, hist_r, hist_alive = [], [], []
+    total_moves = torch.zeros(1, dtype=torch.int64, device=dev)
+    blob = prec = None
+    if model is not None:
+        blob, prec = blob_for(model, precision)
+    step = 0
+    while step < max_steps:
+        if model is None:
+            res = torch.zeros((G, 4), dtype=torch.float64, device=dev)
+            for t in range(times):
+                r = _dist.mcts_fixed_sharded(boards, number, s, _eval_ids(step * times + t, G), group)
+                res += r["min"].to(torch.float64)
+            res /= times
+        else:
+            r = _dist.mcts_nn_sharded(blob, prec, boards, number, s, _eval_ids(step, G), group)
+            res = r["min"].to(torch.float64)
+            total_moves += r["total_moves"]
+        choice = res.argmax(dim=1).to(torch.uint8)  # np.argmax: first maximum (selfplay.py:39,95)
+        nb, gain, moved = engine.move_batch(boards, choice)
+        adv = alive & moved.to(torch.bool)  # game over when the argmax move is illegal (selfplay.py:40-42)
+        hist_b.append(boards.clone())
+        hist_r.append(res.to(torch.float32))
+        hist_alive.append(adv.clone())
+        spawned, _ = engine.spawn_batch(torch.where(adv, nb, boards), s, gids=gids, k=kmain)
+        boards = torch.where(adv, spawned, boards)
+        score += torch.where(adv, gain.to(torch.int64), torch.zeros_like(score))
+        kmain += adv.to(torch.int32)
+        alive = adv
+        step += 1
+        if not bool(alive.any().item()):  # the one host read per main step
+            break
+    hb = torch.stack(hist_b).cpu().numpy().view(np.uint64)  # [T, G]
+    hr = torch.stack(hist_r).cpu().numpy()
+    ha = torch.stack(hist_alive).cpu().numpy()
+    sc = score.cpu().numpy()
+    records = []
+    for g in range(G):
+        T = int(ha[:, g].sum())  # steps are contiguous from 0 while the game advances
+        records.append(dict(boards=hb[:T, g].copy(), results=hr[:T, g].copy(), score=int(sc[g])))
+    return records, int(total_moves.item())
+
+
+def save_record(path, rec):
+    """selfplay.py:55-58 / 111-114 npz format."""
+    np.savez(path, boards=np.asarray(rec["boards"], dtype=np.uint64), results=np.asarray(rec["results"], dtype=np.float32),
+             score=rec["score"])
+
+
+def selfplay_fixed(name, board=None, number=10, times=1, verbose=False, seed=None, out_dir='selfplay/fixed10/'):
+    """selfplay.py:9-59 (single main game, fixed-order min-move search)."""
+    print(f'fixed {number} lines, {times} times')
+    starts = None if not board else torch.from_numpy(np.array([board], np.uint64).view(np.int64))
+    recs, _ = selfplay_batch(1, number, None, times, seed, starts=starts)
+    rec = recs[0]
+    print('Score {}'.format(rec["score"]))
+    print('{} moves'.format(len(rec["boards"])))
+    os.makedirs(out_dir, exist_ok=True)
+    save_record(os.path.join(out_dir, name), rec)
+    print('Saved as {}.npz'.format(name))
+    return rec
+
+
+def selfplay(name, model, board=None, number=10, device='cuda', verbose=False, seed=None, out_dir='selfplay/'):
+    """selfplay.py:62-115 (single main game, mcts_nn search)."""
+    print('Seed {}'.format(name))
+    starts = None if not board else torch.from_numpy(np.array([board], np.uint64).view(np.int64))
+    recs, _ = selfplay_batch(1, number, model, 1, seed, starts=starts)
+    rec = recs[0]
+    print('Score {}'.format(rec["score"]))
+    print('{} moves'.format(len(rec["boards"])))
+    os.makedirs(out_dir, exist_ok=True)
+    save_record(os.path.join(out_dir, name), rec)
+    print('Saved {}.npz'.format(name))
+    return rec

@@ -1,0 +1,100 @@
+"""CPU (gloo, world_size 2): the multi-GPU host logic -- line sharding and the root-statistics
+allreduce -- reproduces the unsharded result bit-for-bit.  Per-rank partials come from the oracle
+(the CUDA kernels need a GPU; their sharding invariance is checked in test_engine_gpu.py)."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _partial(oracle, origins, number, seed, begin, end):
+    G = len(origins)
+    legal = np.zeros((G, 4), np.uint8)
+    logsum = np.zeros((G, 4), np.int64)
+    count = np.zeros((G, 4), np.int32)
+    minmov = np.full((G, 4), 2**31 - 1, np.int32)
+    for g, o in enumerate(origins):
+        lg, rs, sc, mv, _ = oracle.root_lines(int(o), number, seed, g)
+        legal[g] = lg
+        for i in range(4):
+            if lg[i] and end > begin:
+                t = np.log10(sc[i, begin:end].astype(np.float64) + float(rs[i]) + 1.0)
+                logsum[g, i] = np.rint(np.ldexp(t, 40)).astype(np.int64).sum()
+                count[g, i] = end - begin
+                minmov[g, i] = mv[i, begin:end].min()
+    return legal, logsum, count, minmov
+
+
+def _worker(rank, world_size, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from oracle import oracle
+
+    d = importlib.import_module("2048nn_b200.dist")
+    origins = [0x2141348, 0x0000000100000001, 0x1111222233334444, 0x21]
+    number, seed = 7, 4242
+    b, e = d.shard_lines(number, rank, world_size)
+    legal, logsum, count, minmov = _partial(oracle, origins, number, seed, b, e)
+    stats = dict(logsum=torch.from_numpy(logsum), count=torch.from_numpy(count), minmov=torch.from_numpy(minmov))
+    d.allreduce_root_stats(stats)
+    mean = d.mean_log_from_stats(torch.from_numpy(legal), stats["logsum"], stats["count"])
+    mn = d.min_from_stats(torch.from_numpy(legal), stats["minmov"])
+    q.put((rank, (b, e), stats["logsum"].numpy().copy(), stats["count"].numpy().copy(), mean.numpy().copy(), mn.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_lines_partition():
+    d = importlib.import_module("2048nn_b200.dist")
+    for number in (1, 7, 10, 50):
+        for ws in (1, 2, 3, 8):
+            parts = [d.shard_lines(number, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == number
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_allreduce_root_stats_world2(orc):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    out.sort(key=lambda t: t[0])
+    assert out[0][1] == (0, 4) and out[1][1] == (4, 7)
+    # every rank holds the same reduced statistics ...
+    for k in range(2, 6):
+        assert np.array_equal(out[0][k], out[1][k])
+    # ... equal to the unsharded evaluation
+    origins = [0x2141348, 0x0000000100000001, 0x1111222233334444, 0x21]
+    legal, logsum, count, minmov = _partial(orc, origins, 7, 4242, 0, 7)
+    assert np.array_equal(out[0][2], logsum) and np.array_equal(out[0][3], count)
+    for g, o in enumerate(origins):
+        want_min = orc.mcts_fixed_min(o, 7, 4242, g)
+        assert out[0][5][g].tolist() == want_min
+        want_mean = orc.mcts_fixed(o, 7, 4242, g)
+        assert np.allclose(out[0][4][g], [float(x) for x in want_mean], atol=1e-10, rtol=0)
