@@ -124,3 +124,29 @@ def test_global_random_seed_reproducibility(board):
     random.seed(5)
     b = board.play_fixed_batch(64)
     assert a == b and len(a) == 64
+
+
+def test_bare_name_shims_run_reference_style_script(tmp_path):
+    # the reference's scripts import by bare module name (selfplay.py:3-6)
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from board import *\n"
+        "from mcts import mcts_fixed_min\n"
+        "from network import ConvNet\n"
+        "random.seed(7)\n"
+        "b = generate_init_tiles()\n"
+        "r = mcts_fixed_min(b, 4)\n"
+        "f, s, m = move(b, int(np.argmax(r)))\n"
+        "assert m and len(r) == 4\n"
+        "arr = BoardArray([generate_tile(f) for _ in range(5)])\n"
+        "while arr.boards:\n"
+        "    arr.move_batch([(0, 1, 3, 2)] * len(arr.boards))\n"
+        "print('ok', sum(p.numel() for p in ConvNet(64, 3).parameters()))\n" % os.path.join(root, "2048nn_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ok 231820" in out.stdout
