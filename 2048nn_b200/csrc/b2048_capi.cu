@@ -82,9 +82,12 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CK(cudaFuncSetAttribute(convnet_fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             CN_FP32_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::convnet_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(playout_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(playout_nn_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_FP32_SMEM_BYTES));
     *out = c;
     return 0;
@@ -288,6 +291,27 @@ static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st) {
     return 0;
 }
 
+static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logp, float *out_logits,
+                             float *dbg, int dbg_layer, int64_t n, cudaStream_t st) {
+    tc::FwdWork::Params p;
+    p.boards = (const unsigned long long *)boards;
+    p.out_logp = out_logp;
+    p.out_logits = out_logits;
+    p.n = (long)n;
+    unsigned slot = (c->next_counter++) % N_COUNTERS;
+    p.counter = c->counters + slot;
+    CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
+    int grid = grid_for(n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+    if (dbg)
+        tc::tc_persistent_kernel<tc::FwdWork, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            p, (const uint8_t *)blob, dbg, dbg_layer, (long)n);
+    else
+        tc::tc_persistent_kernel<tc::FwdWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            p, (const uint8_t *)blob, nullptr, -1, (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *blob, const uint64_t *boards,
                                      float *out_logp, int64_t n, void *stream) {
     if (n <= 0) return 0;
@@ -300,19 +324,7 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
         CK(cudaGetLastError());
         return 0;
     }
-    if (precision == B2048_PREC_FP16_TC) {
-        tc::FwdParams p;
-        memset(&p, 0, sizeof p);
-        p.blob = (const uint8_t *)blob;
-        p.boards = (const unsigned long long *)boards;
-        p.out_logp = out_logp;
-        p.n = (long)n;
-        p.dbg_layer = -1;
-        int grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
-        tc::convnet_tc_forward_kernel<<<grid, 320, tc::SMEM_BYTES, st>>>(p);
-        CK(cudaGetLastError());
-        return 0;
-    }
+    if (precision == B2048_PREC_FP16_TC) return launch_tc_forward(c, blob, boards, out_logp, nullptr, nullptr, -1, n, st);
     return fail_msg("b2048_convnet_forward: unknown precision");
 }
 
@@ -321,18 +333,7 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
 extern "C" int b2048_convnet_tc_debug(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logits,
                                       float *dbg, int dbg_layer, int64_t n, void *stream) {
     if (n <= 0) return 0;
-    tc::FwdParams p;
-    memset(&p, 0, sizeof p);
-    p.blob = (const uint8_t *)blob;
-    p.boards = (const unsigned long long *)boards;
-    p.out_logits = out_logits;
-    p.n = (long)n;
-    p.dbg = dbg;
-    p.dbg_layer = dbg ? dbg_layer : -1;
-    int grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
-    tc::convnet_tc_forward_kernel<<<grid, 320, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
-    return 0;
+    return launch_tc_forward(c, blob, boards, nullptr, out_logits, dbg, dbg ? dbg_layer : -1, n, (cudaStream_t)stream);
 }
 
 static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t st) {
@@ -348,8 +349,9 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         return 0;
     }
     if (precision == B2048_PREC_FP16_TC) {
-        int grid = grid_for(p.n, tc::TILE_BOARDS, c->num_sms);
-        playout_nn_tc_kernel<<<grid, 320, tc::SMEM_BYTES, st>>>(p);
+        int grid = grid_for(p.n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+        tc::tc_persistent_kernel<PlayWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, (const uint8_t *)p.blob, nullptr,
+                                                                                    -1, 0);
         CK(cudaGetLastError());
         return 0;
     }

@@ -12,7 +12,8 @@
 //   * One A operand feeds up to three output columns: for input slab s and a given dy,
 //     D[x=s-1 | x=s | x=s+1] += A(s,dy) * [W(dy,+1); W(dy,0); W(dy,-1)]^T is ONE
 //     tcgen05.mma with N = 192 (128 at the borders) into adjacent TMEM column blocks.
-//   * Accumulators: TMEM, 4 column blocks x 64 fp32 columns (one per board column x).
+//   * Accumulators: TMEM, per tile-set 4 column blocks x 64 fp32 columns (one per board column x);
+//     two tile-sets = all 512 columns.
 //   * Weights (fp16, BatchNorm folded) stream from L2 as 24 KB pre-swizzled chunks
 //     [W(dy,+1); W(dy,0); W(dy,-1)] through a cp.async.bulk + mbarrier ring.
 //   * Epilogue warps: tcgen05.ld -> +bias (+residual) -> ReLU -> fp16 -> swizzled st.shared
@@ -20,8 +21,16 @@
 //   * L0 (one-hot input, 16 channels) is made exact on the tensor cores by splitting its folded
 //     weights into fp16 hi + lo and feeding the one-hot row twice along K (K = 32).
 //
-// Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2..9 = workers (encode boards, epilogues, head).
+//   * Two tile-sets (A, B) per CTA in ping-pong: while the tensor pipe runs layer L of set A, the
+//     epilogue warps of set B drain layer L-1 of B (and vice versa), and in the playout kernel the
+//     board-engine phase of one set hides behind the other set's network.  Activations are updated
+//     IN PLACE (one 84 KB image per set: all MMAs of a layer retire before its epilogue starts);
+//     the residual input of a block stays in the epilogue threads' registers as packed fp16.
+//
+// Warp roles (640 threads): warps 0..7 = workers of set A, warps 8..15 = workers of set B (encode,
+// epilogues, head; the first warp of each group also owns the set's 32 boards / game slots),
+// warp 16 = weight producer, warp 17 = MMA issuer (+TMEM owner), warps 18..19 idle.  setmaxnreg
+// moves registers from the control warpgroup to the four worker warpgroups.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -41,7 +50,15 @@ constexpr int CHUNK_BYTES = CHUNK_ROWS * ROW_BYTES;  // 24,576
 constexpr int N_LAYERS = 7;                        // L0 + 6 residual-block convs
 constexpr int N_CHUNKS = N_LAYERS * 3;
 constexpr int RING = 2;
-constexpr int TMEM_COLS = 256;
+constexpr int NSETS = 2;                          // tile-sets in flight per CTA (ping-pong)
+constexpr int GROUP_WARPS = 8;                    // worker warps per tile-set
+constexpr int WORKER_WARPS = NSETS * GROUP_WARPS;  // warps 0..15
+constexpr int PRODUCER_WARP = WORKER_WARPS;       // warp 16
+constexpr int MMA_WARP = WORKER_WARPS + 1;        // warp 17 (18, 19 idle: whole warpgroup for setmaxnreg)
+constexpr int NUM_WARPS = WORKER_WARPS + 4;
+constexpr int NUM_THREADS = NUM_WARPS * 32;       // 640
+constexpr int WORKER_REGS = 112, CONTROL_REGS = 32;  // setmaxnreg pool = launch allocation 640 x 96: 16*32*112 + 4*32*32 = 61,440
+constexpr int TMEM_COLS = 512;
 
 // blob: [21 chunks fp16, pre-swizzled] [fp32 tail: bias 7x64 | w7 4x64 | b7 4 | fcw 4x64 | fcb 4]
 constexpr int BLOB_W_BYTES = N_CHUNKS * CHUNK_BYTES;
@@ -50,15 +67,16 @@ constexpr int TAIL_BIAS = 0, TAIL_W7 = 7 * 64, TAIL_B7 = TAIL_W7 + 256, TAIL_FCW
 constexpr int BLOB_BYTES = BLOB_W_BYTES + TAIL_FLOATS * 4;
 
 // shared memory map (offsets from a 1024-aligned base)
-constexpr int SM_ACT_A = 0;
-constexpr int SM_ACT_B = SM_ACT_A + ACT_BYTES;
-constexpr int SM_RING = SM_ACT_B + ACT_BYTES;            // 172,032 (1024-aligned)
-constexpr int SM_TAIL = SM_RING + RING * CHUNK_BYTES;    // fp32 tail copy
-constexpr int SM_BOARDS = SM_TAIL + TAIL_FLOATS * 4;     // 32 x u64
-constexpr int SM_LOGITS = SM_BOARDS + 32 * 8;            // 32 x 4 f32
-constexpr int SM_BARS = SM_LOGITS + 32 * 16;             // mbarriers
-constexpr int SM_TOTAL = SM_BARS + 16 * RING + 16 + 16;  // ring full/empty, acc, act, tmem base
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;              // + alignment slack
+constexpr int SM_ACT = 0;                                  // NSETS in-place activation images
+constexpr int SM_RING = SM_ACT + NSETS * ACT_BYTES;        // 172,032 (1024-aligned)
+constexpr int SM_TAIL = SM_RING + RING * CHUNK_BYTES;      // fp32 tail copy
+constexpr int SM_BOARDS = SM_TAIL + TAIL_FLOATS * 4;       // NSETS x 32 x u64
+constexpr int SM_LOGITS = SM_BOARDS + NSETS * 32 * 8;      // NSETS x 32 x 4 f32
+constexpr int SM_RUN = SM_LOGITS + NSETS * 32 * 16;        // NSETS x {run flag, debug base}
+constexpr int SM_BARS = SM_RUN + 32 * NSETS;                      // mbarriers: full[RING] empty[RING] acc[NSETS] act[NSETS]
+constexpr int SM_TMEMPTR = SM_BARS + 8 * (2 * RING + 2 * NSETS);
+constexpr int SM_TOTAL = SM_TMEMPTR + 16;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
 
 constexpr int HEAD_STRIDE = 65;  // floats per board in the head staging area (bank-conflict padding)
 
@@ -132,6 +150,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -149,113 +182,283 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ uint32_t act_off(int R, int c) { return (uint32_t)R * ROW_BYTES + (uint32_t)((c ^ (R & 7)) << 4); }
 __device__ __forceinline__ int act_row(int x, int y, int b) { return (5 * x + 1 + y) * SLAB_ROWS + b; }
 
-struct FwdParams {
-    const uint8_t *blob;             // BLOB_BYTES image
-    const unsigned long long *boards;  // N boards
-    float *out_logp;                 // N x 4 log-probs (may be NULL)
-    float *out_logits;               // N x 4 pre-softmax (may be NULL)
-    long n;
-    // debug: dump the fp32 post-activation output of layer dbg_layer as [board][co][pos]
-    float *dbg;
-    int dbg_layer;
+
+__device__ __forceinline__ void named_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct Bars {
+    uint32_t full0, empty0, acc0, act0;
+    __device__ __forceinline__ explicit Bars(uint32_t sm_base) {
+        full0 = sm_base + SM_BARS;
+        empty0 = full0 + 8 * RING;
+        acc0 = empty0 + 8 * RING;
+        act0 = acc0 + 8 * NSETS;
+    }
 };
 
-// The CTA-wide forward of one tile-set.  Called by ALL 320 threads; `s_boards` holds the 32
-// boards (0 for unused slots), logits land in `s_logits` [32][4].
-// Pipeline state (ring slot / phases) persists across calls in `st`.
-struct PipeState {
-    uint32_t ring_prod;  // chunks produced
-    uint32_t ring_cons;  // chunks consumed
-    uint32_t layer_phase;  // parity of acc_full / act_ready
-};
-
-__device__ __forceinline__ void forward_tile(uint8_t *sm, uint32_t tmem_base, const uint8_t *blob, PipeState &st,
-                                             float *dbg, int dbg_layer, long dbg_base, int dbg_n) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// ---- CTA setup / teardown ----------------------------------------------------------------------
+__device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *blob, uint32_t &tmem_base) {
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sm_base = smem_u32(sm);
-    const uint32_t bar_full0 = sm_base + SM_BARS;          // ring full  [RING]
-    const uint32_t bar_empty0 = bar_full0 + 8 * RING;      // ring empty [RING]
-    const uint32_t bar_acc = bar_empty0 + 8 * RING;        // accumulators complete
-    const uint32_t bar_act = bar_acc + 8;                  // layer input ready (8 worker warps)
-    const float *tail = reinterpret_cast<const float *>(sm + SM_TAIL);
-    const unsigned long long *s_boards = reinterpret_cast<const unsigned long long *>(sm + SM_BOARDS);
-    float *s_logits = reinterpret_cast<float *>(sm + SM_LOGITS);
+    const int tid = threadIdx.x;
+    // zero the activation images (the zero slabs stay zero for the kernel's lifetime)
+    for (int i = tid; i < NSETS * ACT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    const float *gtail = reinterpret_cast<const float *>(blob + BLOB_W_BYTES);
+    for (int i = tid; i < TAIL_FLOATS; i += blockDim.x) reinterpret_cast<float *>(sm + SM_TAIL)[i] = gtail[i];
+    if (tid == 0) {
+        Bars b(sm_base);
+        for (int i = 0; i < RING; i++) {
+            mbar_init(b.full0 + 8 * i, 1);
+            mbar_init(b.empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < NSETS; i++) {
+            mbar_init(b.acc0 + 8 * i, 1);            // tcgen05.commit
+            mbar_init(b.act0 + 8 * i, GROUP_WARPS);  // one arrival per worker warp of the set
+        }
+        fence_mbar_init();
+    }
+    if ((tid >> 5) == MMA_WARP) tmem_alloc(sm_base + SM_TMEMPTR, TMEM_COLS);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_TMEMPTR);
+    return sm;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
 
-    if (warp == 0) {
-        // ===== weight producer: 21 chunks per tile-set through the ring ========================
-        if (lane == 0) {
-            for (int c = 0; c < N_CHUNKS; c++) {
-                uint32_t slot = st.ring_prod % RING, use = st.ring_prod / RING;
-                if (use > 0) mbar_wait(bar_empty0 + 8 * slot, (use - 1) & 1);
-                mbar_expect_tx(bar_full0 + 8 * slot, CHUNK_BYTES);
-                bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
-                         bar_full0 + 8 * slot);
-                st.ring_prod++;
-            }
-        }
-        st.ring_prod = __shfl_sync(0xffffffffu, st.ring_prod, 0);
-    } else if (warp == 1) {
-        // ===== MMA issuer ===========================================================================
-        uint32_t phase = st.layer_phase;
+// ---- warp 0: weight producer ---------------------------------------------------------------------
+// Mirrors the MMA warp's control flow: per forward of a set, 7 layers x 3 chunks through the ring.
+__device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) {
+    const uint32_t sm_base = smem_u32(sm);
+    const Bars bars(sm_base);
+    const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
+    const int lane = threadIdx.x & 31;
+    bool active[NSETS];
+    uint32_t iter[NSETS];
+    for (int i = 0; i < NSETS; i++) active[i] = true, iter[i] = 0;
+    uint32_t prod = 0;
+    while (active[0] || active[1]) {
         for (int l = 0; l < N_LAYERS; l++) {
-            // layer input: l even (incl. L0, whose input is the one-hot image) reads B, l odd reads A
-            const uint32_t in_addr = sm_base + ((l & 1) ? SM_ACT_A : SM_ACT_B);
-            mbar_wait(bar_act, phase & 1);  // workers finished writing this layer's input
-            tc_fence_after();
-            const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
-            for (int dyi = 0; dyi < 3; dyi++) {
-                uint32_t slot = st.ring_cons % RING, use = st.ring_cons / RING;
-                mbar_wait(bar_full0 + 8 * slot, use & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t w_addr = sm_base + SM_RING + slot * CHUNK_BYTES;
-#pragma unroll 1
-                    for (int si = 0; si < 4; si++) {
-                        // slab order 0,3,1,2: the k==0 MMAs of slabs 0 and 3 (dy=-1) are the first writers
-                        // of column blocks {0,1} and {2,3}, so they overwrite; everything else accumulates.
-                        const int s = (si == 0) ? 0 : (si == 1) ? 3 : si - 1;
-                        const int x_lo = s > 0 ? s - 1 : 0, x_hi = s < 3 ? s + 1 : 3;
-                        const int N = (x_hi - x_lo + 1) * 64;   // 128 at the borders, 192 inside
-                        const int brow = (s == 0) ? 64 : 0;     // rows [dx=+1|dx=0|dx=-1]: drop dx=+1 for s==0
-                        const uint32_t idesc = make_idesc(128, N);
-                        const uint32_t a_addr = in_addr + (uint32_t)((5 * s + dyi) * SLAB_ROWS) * ROW_BYTES;
-                        const uint32_t b_addr = w_addr + (uint32_t)brow * ROW_BYTES;
-                        const uint32_t d_addr = tmem_base + (uint32_t)(x_lo * 64);
-                        for (int k = 0; k < nk; k++) {
-                            const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
-                            umma_f16(d_addr, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, acc);
-                        }
+            for (int set = 0; set < NSETS; set++) {
+                if (!active[set]) continue;
+                if (l == 0) {  // the set's workers publish "run" before their first act_ready arrival
+                    mbar_wait(bars.act0 + 8 * set, (iter[set] * N_LAYERS) & 1);
+                    if (!s_run[8 * set]) {
+                        active[set] = false;
+                        continue;
                     }
-                    umma_commit(bar_empty0 + 8 * slot);  // ring slot reusable once these MMAs retire
                 }
-                __syncwarp();
-                st.ring_cons++;
+                if (lane == 0) {
+                    for (int dyi = 0; dyi < 3; dyi++) {
+                        const uint32_t slot = prod % RING, use = prod / RING;
+                        if (use > 0) mbar_wait(bars.empty0 + 8 * slot, (use - 1) & 1);
+                        mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES);
+                        bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)(l * 3 + dyi) * CHUNK_BYTES,
+                                 CHUNK_BYTES, bars.full0 + 8 * slot);
+                        prod++;
+                    }
+                }
+                if (l == N_LAYERS - 1) iter[set]++;
             }
-            if (lane == 0) umma_commit(bar_acc);
-            __syncwarp();
-            phase++;
         }
-        st.layer_phase = phase;
-    } else {
-        // ===== workers: 8 warps, thread <-> (y = warp%4 TMEM quarter, board = lane), 2 x-tiles ======
-        const int q = warp & 3;                 // TMEM lane quarter this warp may read == board row y
-        const int xg = (warp - 2) >> 2;         // 0: x in {0,1}; 1: x in {2,3}
-        uint32_t phase = st.layer_phase;
-        // ---- encode: one-hot rows of buffer B (channels [0,16) and again [16,32) for the hi/lo split)
+    }
+}
+
+// ---- warp 1: MMA issuer -----------------------------------------------------------------------------
+__device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
+    const uint32_t sm_base = smem_u32(sm);
+    const Bars bars(sm_base);
+    const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
+    const int lane = threadIdx.x & 31;
+    bool active[NSETS];
+    uint32_t phase[NSETS];
+    for (int i = 0; i < NSETS; i++) active[i] = true, phase[i] = 0;
+    uint32_t cons = 0;
+    while (active[0] || active[1]) {
+        for (int l = 0; l < N_LAYERS; l++) {
+            for (int set = 0; set < NSETS; set++) {
+                if (!active[set]) continue;
+                mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
+                if (l == 0 && !s_run[8 * set]) {
+                    active[set] = false;
+                    continue;
+                }
+                tc_fence_after();
+                const uint32_t in_addr = sm_base + SM_ACT + set * ACT_BYTES;
+                const uint32_t acc_base = tmem_base + (uint32_t)(set * 256);
+                const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
+                for (int dyi = 0; dyi < 3; dyi++) {
+                    const uint32_t slot = cons % RING, use = cons / RING;
+                    mbar_wait(bars.full0 + 8 * slot, use & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t w_addr = sm_base + SM_RING + slot * CHUNK_BYTES;
+#pragma unroll 1
+                        for (int si = 0; si < 4; si++) {
+                            // slab order 0,3,1,2: the (dy=-1, k=0) MMAs of slabs 0 and 3 are the first writers of
+                            // column blocks {0,1} and {2,3}: they overwrite, everything else accumulates.
+                            const int s = (si == 0) ? 0 : (si == 1) ? 3 : si - 1;
+                            const int x_lo = s > 0 ? s - 1 : 0, x_hi = s < 3 ? s + 1 : 3;
+                            const int N = (x_hi - x_lo + 1) * 64;  // 128 at the borders, 192 inside
+                            const int brow = (s == 0) ? 64 : 0;    // rows [dx=+1|dx=0|dx=-1]: no dx=+1 for s==0
+                            const uint32_t idesc = make_idesc(128, N);
+                            const uint32_t a_addr = in_addr + (uint32_t)((5 * s + dyi) * SLAB_ROWS) * ROW_BYTES;
+                            const uint32_t b_addr = w_addr + (uint32_t)brow * ROW_BYTES;
+                            const uint32_t d_addr = acc_base + (uint32_t)(x_lo * 64);
+                            for (int k = 0; k < nk; k++) {
+                                const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
+                                umma_f16(d_addr, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, acc);
+                            }
+                        }
+                        umma_commit(bars.empty0 + 8 * slot);  // ring slot reusable once these MMAs retire
+                    }
+                    __syncwarp();
+                    cons++;
+                }
+                if (lane == 0) umma_commit(bars.acc0 + 8 * set);
+                __syncwarp();
+                phase[set]++;
+            }
+        }
+    }
+}
+
+// Epilogue of one conv layer for the two rows (x0, y, lane), (x0+1, y, lane) a worker thread owns:
+// TMEM -> +bias (+residual) -> ReLU -> fp16 -> swizzled st.shared (next layer's A operand, in place).
+// The layer kind is a compile-time parameter so the hot loop carries no dead code:
+//   ADD_RES  second conv of a block: add the block input kept in `res`
+//   KEEP_RES this output is a block input: remember it (packed fp16) in `res`
+//   LAST     last conv: do not write back; accumulate the 1x1 head conv on the fp32 values instead
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
+__device__ __forceinline__ void epilogue_layer(uint8_t *row0, uint8_t *row1, int sw, const float *bias, const float *tail,
+                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
+                                               float *dbg0) {
+    // register budget: res (64) dominates, so TMEM is drained 8 columns x 2 rows at a time
+#pragma unroll
+    for (int c = 0; c < 8; c++) {  // 16-byte chunk = 8 channels
+        float v[2][8];
+        tmem_ld8(acc0 + (uint32_t)(c * 8), reinterpret_cast<uint32_t *>(v[0]));
+        tmem_ld8(acc0 + (uint32_t)(64 + c * 8), reinterpret_cast<uint32_t *>(v[1]));
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        tmem_ld_wait();
+#pragma unroll
+        for (int xi = 0; xi < 2; xi++) {
+            uint4 pk;
+            uint32_t *pw = &pk.x;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                float a0 = v[xi][2 * jj] + bb[2 * jj];
+                float a1 = v[xi][2 * jj + 1] + bb[2 * jj + 1];
+                if (ADD_RES) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
+                    a0 += f.x, a1 += f.y;
+                }
+                a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
+                if (LAST || DBG) v[xi][2 * jj] = a0, v[xi][2 * jj + 1] = a1;
+                if (!LAST) {
+                    const __half2 hh = __floats2half2_rn(a0, a1);
+                    pw[jj] = *reinterpret_cast<const uint32_t *>(&hh);
+                    if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
+                }
+            }
+            if (!LAST) *reinterpret_cast<uint4 *>((xi ? row1 : row0) + ((c ^ sw) << 4)) = pk;
+            if (DBG && dbg0) {
+#pragma unroll
+                for (int co = 0; co < 8; co++) dbg0[((c * 8 + co) * 16) + xi] = v[xi][co];
+            }
+            if (LAST) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const float4 t0 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8);
+                    const float4 t1 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8 + 4);
+                    float sacc = head_acc[xi][c4];
+                    sacc = fmaf(v[xi][0], t0.x, sacc), sacc = fmaf(v[xi][1], t0.y, sacc);
+                    sacc = fmaf(v[xi][2], t0.z, sacc), sacc = fmaf(v[xi][3], t0.w, sacc);
+                    sacc = fmaf(v[xi][4], t1.x, sacc), sacc = fmaf(v[xi][5], t1.y, sacc);
+                    sacc = fmaf(v[xi][6], t1.z, sacc), sacc = fmaf(v[xi][7], t1.w, sacc);
+                    head_acc[xi][c4] = sacc;
+                }
+            }
+        }
+    }
+}
+
+
+// ---- worker groups -----------------------------------------------------------------------------------
+// Work policy (owner warp = first warp of a group, all 32 lanes call it):
+//   struct Work { struct Params; struct State;
+//     static void init(State&);
+//     // consume the previous forward's outputs (unless first), then provide the next 32 boards.
+//     // returns false when the set is finished.
+//     static bool step(const Params&, State&, bool first, const float *logits, unsigned long long *boards,
+//                      int lane, long &dbg_base); };
+template <class Work, bool DBG>
+__device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, const typename Work::Params &wp, int set,
+                                            int j, float *dbg, int dbg_layer, long dbg_n) {
+    const uint32_t sm_base = smem_u32(sm);
+    const Bars bars(sm_base);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read == board row y
+    const int xg = j >> 2;    // rows handled: x in {2*xg, 2*xg+1}
+    uint8_t *act = sm + SM_ACT + set * ACT_BYTES;
+    const float *tail = reinterpret_cast<const float *>(sm + SM_TAIL);
+    unsigned long long *s_boards = reinterpret_cast<unsigned long long *>(sm + SM_BOARDS) + set * 32;
+    float *s_logits = reinterpret_cast<float *>(sm + SM_LOGITS) + set * 128;
+    volatile int *s_run = reinterpret_cast<volatile int *>(sm + SM_RUN) + 8 * set;
+    volatile long *s_dbgbase = reinterpret_cast<volatile long *>(sm + SM_RUN + 32 * set + 8);
+    const uint32_t bar_acc = bars.acc0 + 8 * set, bar_act = bars.act0 + 8 * set;
+    // accumulators of this thread's two rows: lane quarter q, column blocks x0 and x0+1 of the set
+    const uint32_t acc0 = tmem_base + (uint32_t)(set * 256 + xg * 128) + ((uint32_t)(q * 32) << 16);
+    uint8_t *row0 = act + (size_t)act_row(2 * xg, q, lane) * ROW_BYTES;
+    uint8_t *row1 = act + (size_t)act_row(2 * xg + 1, q, lane) * ROW_BYTES;
+    const int sw = lane & 7;  // SWIZZLE_128B phase of both rows (row index % 8 == lane % 8)
+    const int bar_id = 1 + set;
+    typename Work::State ws;
+    if (j == 0) Work::init(ws);
+    uint32_t phase = 0;
+    bool first = true;
+    uint32_t res[2][32];  // residual input of the current block, packed fp16
+    for (;;) {
+        if (j == 0) {
+            long db = 0;
+            bool run = Work::step(wp, ws, first, s_logits, s_boards, lane, db);
+            if (lane == 0) {
+                *s_run = run ? 1 : 0;
+                *s_dbgbase = db;
+            }
+        }
+        first = false;
+        named_bar(bar_id, GROUP_WARPS * 32);
+        const bool run = *s_run != 0;
+        if (!run) {
+            if (lane == 0) mbar_arrive(bar_act);  // tells the MMA / producer warps that this set is done
+            break;
+        }
+        // ---- encode: one-hot rows (channels [0,16) and again [16,32) for the hi/lo weight split) --------
         {
             const unsigned long long brd = s_boards[lane];
+#pragma unroll
             for (int xi = 0; xi < 2; xi++) {
-                const int x = xg * 2 + xi, y = q;
-                const int t = (int)((brd >> (4 * (y * 4 + x))) & 0xF);
-                const int R = act_row(x, y, lane);
-                uint4 lo8 = make_uint4(0, 0, 0, 0), hi8 = make_uint4(0, 0, 0, 0);
+                const int t = (int)((brd >> (4 * (q * 4 + 2 * xg + xi))) & 0xF);
+                uint8_t *row = xi ? row1 : row0;
                 const uint32_t one = 0x3C00u << ((t & 1) * 16);  // fp16 1.0 in the right half-word
-                uint32_t *dst = (t < 8) ? &lo8.x : &hi8.x;
-                dst[(t & 7) >> 1] = one;
-                *reinterpret_cast<uint4 *>(sm + SM_ACT_B + act_off(R, 0)) = lo8;
-                *reinterpret_cast<uint4 *>(sm + SM_ACT_B + act_off(R, 1)) = hi8;
-                *reinterpret_cast<uint4 *>(sm + SM_ACT_B + act_off(R, 2)) = lo8;
-                *reinterpret_cast<uint4 *>(sm + SM_ACT_B + act_off(R, 3)) = hi8;
+                const int wsel = (t & 7) >> 1;
+                const uint4 hot = make_uint4(wsel == 0 ? one : 0u, wsel == 1 ? one : 0u, wsel == 2 ? one : 0u,
+                                             wsel == 3 ? one : 0u);
+                const uint4 zero = make_uint4(0, 0, 0, 0);
+                const uint4 lo8 = (t < 8) ? hot : zero, hi8 = (t < 8) ? zero : hot;
+                *reinterpret_cast<uint4 *>(row + ((0 ^ sw) << 4)) = lo8;
+                *reinterpret_cast<uint4 *>(row + ((1 ^ sw) << 4)) = hi8;
+                *reinterpret_cast<uint4 *>(row + ((2 ^ sw) << 4)) = lo8;
+                *reinterpret_cast<uint4 *>(row + ((3 ^ sw) << 4)) = hi8;
             }
         }
         fence_proxy_async();
@@ -263,154 +466,117 @@ __device__ __forceinline__ void forward_tile(uint8_t *sm, uint32_t tmem_base, co
         if (lane == 0) mbar_arrive(bar_act);
 
         float head_acc[2][4];
+#pragma unroll
+        for (int xi = 0; xi < 2; xi++)
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) head_acc[xi][c4] = tail[TAIL_B7 + c4];
+        float *dbg0 = nullptr;
+#pragma unroll 1
         for (int l = 0; l < N_LAYERS; l++) {
-            uint8_t *out = sm + (((l & 1) == 0) ? SM_ACT_A : SM_ACT_B);  // l=0 ->A, l=1 ->B, l=2 ->A ...
-            const bool residual = (l >= 2) && ((l & 1) == 0);           // second conv of a block writes A in place
-            const bool last = (l == N_LAYERS - 1);
+            const float *bias = tail + TAIL_BIAS + l * 64;
             mbar_wait(bar_acc, phase & 1);
             tc_fence_after();
-            for (int xi = 0; xi < 2; xi++) {
-                const int x = xg * 2 + xi, y = q;
-                const int R = act_row(x, y, lane);
-                float v[64];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * 64), reinterpret_cast<uint32_t *>(v));
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * 64 + 32),
-                          reinterpret_cast<uint32_t *>(v + 32));
-                tmem_ld_wait();
-                const float *bias = tail + TAIL_BIAS + l * 64;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    if (residual) {
-                        uint4 xr = *reinterpret_cast<const uint4 *>(out + act_off(R, c));
-                        const __half2 *h = reinterpret_cast<const __half2 *>(&xr);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float2 f = __half22float2(h[j]);
-                            r[2 * j] = f.x, r[2 * j + 1] = f.y;
-                        }
-                    }
-                    uint4 pk;
-                    __half2 *hp = reinterpret_cast<__half2 *>(&pk);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float a = fmaxf(v[c * 8 + 2 * j] + bias[c * 8 + 2 * j] + r[2 * j], 0.f);
-                        float b2 = fmaxf(v[c * 8 + 2 * j + 1] + bias[c * 8 + 2 * j + 1] + r[2 * j + 1], 0.f);
-                        v[c * 8 + 2 * j] = a, v[c * 8 + 2 * j + 1] = b2;
-                        hp[j] = __floats2half2_rn(a, b2);
-                    }
-                    if (!last) *reinterpret_cast<uint4 *>(out + act_off(R, c)) = pk;
-                }
-                if (dbg && dbg_layer == l && lane < dbg_n) {
-                    float *o = dbg + ((dbg_base + lane) * 64) * 16 + (y * 4 + x);
-#pragma unroll
-                    for (int co = 0; co < 64; co++) o[co * 16] = v[co];
-                }
-                if (last) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        float s = tail[TAIL_B7 + c4];
-                        const float *w = tail + TAIL_W7 + c4 * 64;
-#pragma unroll
-                        for (int ci = 0; ci < 64; ci++) s = fmaf(v[ci], w[ci], s);
-                        head_acc[xi][c4] = fmaxf(s, 0.f);
-                    }
-                }
+            if (DBG) {
+                const long gb = *s_dbgbase + lane;
+                dbg0 = (dbg && dbg_layer == l && gb < dbg_n) ? dbg + gb * 1024 + (q * 4 + 2 * xg) : nullptr;
             }
+            if (l == 0)
+                epilogue_layer<false, true, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
+            else if (l & 1)
+                epilogue_layer<false, false, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
+            else if (l < N_LAYERS - 1)
+                epilogue_layer<true, true, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
+            else
+                epilogue_layer<true, false, true, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
             tc_fence_before();
-            if (!last) {
+            if (l < N_LAYERS - 1) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
             }
             phase++;
         }
-        st.layer_phase = phase;
-        // ---- head: stage [board][c4*16 + pos] in buffer B's first data slab, then FC by warp 2 -------
-        float *hb = reinterpret_cast<float *>(sm + SM_ACT_B + SLAB_ROWS * ROW_BYTES);
+        // ---- head: stage [board][c4*16 + pos] in the image's first data slab, FC by the owner warp --------
+        float *hb = reinterpret_cast<float *>(act + SLAB_ROWS * ROW_BYTES);
+#pragma unroll
         for (int xi = 0; xi < 2; xi++) {
             const int pos = q * 4 + xg * 2 + xi;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) hb[lane * HEAD_STRIDE + c4 * 16 + pos] = head_acc[xi][c4];
+            for (int c4 = 0; c4 < 4; c4++) hb[lane * HEAD_STRIDE + c4 * 16 + pos] = fmaxf(head_acc[xi][c4], 0.f);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 worker warps
-        if (warp == 2) {
+        named_bar(bar_id, GROUP_WARPS * 32);
+        if (j == 0) {
             float z[4];
 #pragma unroll
             for (int o = 0; o < 4; o++) {
-                float s = tail[TAIL_FCB + o];
+                float sacc = tail[TAIL_FCB + o];
                 const float *w = tail + TAIL_FCW + o * 64;
-                for (int j = 0; j < 64; j++) s = fmaf(hb[lane * HEAD_STRIDE + j], w[j], s);
-                z[o] = s;
+#pragma unroll 8
+                for (int jj = 0; jj < 64; jj++) sacc = fmaf(hb[lane * HEAD_STRIDE + jj], w[jj], sacc);
+                z[o] = sacc;
             }
             *reinterpret_cast<float4 *>(s_logits + lane * 4) = make_float4(z[0], z[1], z[2], z[3]);
+            __syncwarp();
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // the owner warp consumes s_logits in Work::step at the top of the loop; the other warps wait for
+        // it at the group barrier there, so the image is not re-encoded before the head has been read.
     }
 }
 
-// ---- CTA setup / teardown shared by the forward and playout kernels ---------------------------
-__device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *blob, uint32_t &tmem_base) {
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t sm_base = smem_u32(sm);
-    const int tid = threadIdx.x;
-    // zero both activation buffers (the zero slabs stay zero for the kernel's lifetime)
-    for (int i = tid; i < 2 * ACT_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
-    const float *gtail = reinterpret_cast<const float *>(blob + BLOB_W_BYTES);
-    for (int i = tid; i < TAIL_FLOATS; i += blockDim.x) reinterpret_cast<float *>(sm + SM_TAIL)[i] = gtail[i];
-    if (tid == 0) {
-        const uint32_t bars = sm_base + SM_BARS;
-        for (int i = 0; i < RING; i++) {
-            mbar_init(bars + 8 * i, 1);           // full
-            mbar_init(bars + 8 * (RING + i), 1);  // empty
-        }
-        mbar_init(bars + 16 * RING, 1);      // acc complete (tcgen05.commit)
-        mbar_init(bars + 16 * RING + 8, 8);  // layer input ready (8 worker warps)
-        fence_mbar_init();
-    }
-    if ((tid >> 5) == 1) tmem_alloc(sm_base + SM_BARS + 16 * RING + 16, TMEM_COLS);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_BARS + 16 * RING + 16);
-    return sm;
-}
-__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
-    tc_fence_before();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// Forward-only kernel (config 5): boards u64[N] -> log-probs f32[N][4].
-__global__ void __launch_bounds__(320, 1) convnet_tc_forward_kernel(const FwdParams p) {
+// Generic persistent kernel: producer + MMA issuer + NSETS worker groups.
+template <class Work, bool DBG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float *dbg, int dbg_layer, long dbg_n) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t tmem_base;
-    uint8_t *sm = tc_setup(smem_raw, p.blob, tmem_base);
-    PipeState st = {0, 0, 0};
-    unsigned long long *s_boards = reinterpret_cast<unsigned long long *>(sm + SM_BOARDS);
-    const float *s_logits = reinterpret_cast<const float *>(sm + SM_LOGITS);
-    const long tiles = (p.n + TILE_BOARDS - 1) / TILE_BOARDS;
-    for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long base = tile * TILE_BOARDS;
-        if (threadIdx.x < TILE_BOARDS) s_boards[threadIdx.x] = (base + threadIdx.x < p.n) ? p.boards[base + threadIdx.x] : 0ULL;
-        __syncthreads();
-        int dbg_n = (int)((p.n - base) < TILE_BOARDS ? (p.n - base) : TILE_BOARDS);
-        forward_tile(sm, tmem_base, p.blob, st, p.dbg, p.dbg_layer, base, dbg_n);
-        __syncthreads();
-        if (threadIdx.x < TILE_BOARDS && base + threadIdx.x < p.n) {
-            float4 z = reinterpret_cast<const float4 *>(s_logits)[threadIdx.x];
-            if (p.out_logits) reinterpret_cast<float4 *>(p.out_logits)[base + threadIdx.x] = z;
-            if (p.out_logp) {
-                float m = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w));
-                float l = m + logf(expf(z.x - m) + expf(z.y - m) + expf(z.z - m) + expf(z.w - m));
-                reinterpret_cast<float4 *>(p.out_logp)[base + threadIdx.x] = make_float4(z.x - l, z.y - l, z.z - l, z.w - l);
-            }
-        }
-        __syncthreads();
+    uint8_t *sm = tc_setup(smem_raw, blob, tmem_base);
+    const int warp = threadIdx.x >> 5;
+    if (warp < WORKER_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
+        worker_loop<Work, DBG>(sm, tmem_base, wp, warp / GROUP_WARPS, warp % GROUP_WARPS, dbg, dbg_layer, dbg_n);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
+        if (warp == PRODUCER_WARP) producer_loop(sm, blob);
+        else if (warp == MMA_WARP) mma_loop(sm, tmem_base);
     }
     tc_teardown(tmem_base);
 }
+
+// ---- work policy of the forward-only kernel (config 5): tiles of 32 boards from a global counter -----
+struct FwdWork {
+    struct Params {
+        const unsigned long long *boards;
+        float *out_logp;    // N x 4 log-probs (may be NULL)
+        float *out_logits;  // N x 4 pre-softmax (may be NULL)
+        long n;
+        unsigned long long *counter;
+    };
+    struct State {
+        long base;
+    };
+    __device__ static void init(State &st) { st.base = -1; }
+    __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
+                                int lane, long &dbg_base) {
+        if (!first && st.base + lane < p.n) {
+            const float4 z = reinterpret_cast<const float4 *>(logits)[lane];
+            if (p.out_logits) reinterpret_cast<float4 *>(p.out_logits)[st.base + lane] = z;
+            if (p.out_logp) {
+                const float m = fmaxf(fmaxf(z.x, z.y), fmaxf(z.z, z.w));
+                const float lse = m + logf(expf(z.x - m) + expf(z.y - m) + expf(z.z - m) + expf(z.w - m));
+                reinterpret_cast<float4 *>(p.out_logp)[st.base + lane] = make_float4(z.x - lse, z.y - lse, z.z - lse, z.w - lse);
+            }
+        }
+        unsigned long long tile = 0;
+        if (lane == 0) tile = atomicAdd(p.counter, 1ULL);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        st.base = (long)tile * TILE_BOARDS;
+        dbg_base = st.base;
+        if (st.base >= p.n) return false;
+        s_boards[lane] = (st.base + lane < p.n) ? p.boards[st.base + lane] : 0ULL;
+        __syncwarp();
+        return true;
+    }
+};
 
 }  // namespace tc
 }  // namespace b2048

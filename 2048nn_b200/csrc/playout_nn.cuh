@@ -166,41 +166,37 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
     if (t < CN_BOARDS_PER_CTA && p.move_counter && moves_done) atomicAdd(p.move_counter, (unsigned long long)moves_done);
 }
 
-// Tensor-core kernel: 32 game slots per CTA (one tile-set of convnet_tc.cuh), 320 threads.
-// Warp 2 owns the slots (lane <-> slot): refill, move choice, spawn; all ten warps run the forward.
-__global__ void __launch_bounds__(320, 1) playout_nn_tc_kernel(const NNPlayParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint32_t tmem_base;
-    uint8_t *sm = tc::tc_setup(smem_raw, reinterpret_cast<const uint8_t *>(p.blob), tmem_base);
-    tc::PipeState st = {0, 0, 0};
-    u64 *s_boards = reinterpret_cast<u64 *>(sm + tc::SM_BOARDS);
-    const float *s_logits = reinterpret_cast<const float *>(sm + tc::SM_LOGITS);
-    __shared__ int s_live;
-    GameSlot g;
-    g.live = 0;
-    g.board = 0;
-    u32 moves_done = 0;
-    bool queue_empty = false;
-    const bool owner = (threadIdx.x >> 5) == 2;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        if (owner) {
-            if (!g.live && !queue_empty) queue_empty = !nn_fetch(p, g);
-            s_boards[lane] = g.live ? g.board : 0ULL;
-            unsigned any = __ballot_sync(0xffffffffu, g.live);
-            if (lane == 0) s_live = any != 0;
+// Tensor-core kernel (tc::tc_persistent_kernel<PlayWork>): 2 x 32 game slots per CTA, one slot per lane
+// of each worker group's owner warp: consume the forward's logits (move choice, spawn, death), refill
+// from the global work counter, hand the next 32 boards to the network.  The engine phase of one set
+// overlaps the other set's forward.
+struct PlayWork {
+    typedef NNPlayParams Params;
+    struct State {
+        GameSlot g;
+        u32 moves_done;
+        bool queue_empty;
+    };
+    __device__ static void init(State &st) {
+        st.g.live = 0;
+        st.g.board = 0;
+        st.moves_done = 0;
+        st.queue_empty = false;
+    }
+    __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
+                                int lane, long &dbg_base) {
+        dbg_base = 0;
+        if (!first && st.g.live) nn_move(p, st.g, logits + 4 * lane, st.moves_done);
+        if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
+        s_boards[lane] = st.g.live ? st.g.board : 0ULL;
+        const unsigned any = __ballot_sync(0xffffffffu, st.g.live);
+        if (!any && p.move_counter) {
+            u32 m = st.moves_done;
+            for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+            if (lane == 0 && m) atomicAdd(p.move_counter, (unsigned long long)m);
         }
-        __syncthreads();
-        if (!s_live) break;
-        tc::forward_tile(sm, tmem_base, reinterpret_cast<const uint8_t *>(p.blob), st, nullptr, -1, 0, 0);
-        __syncthreads();
-        if (owner && g.live) nn_move(p, g, s_logits + 4 * lane, moves_done);
+        return any != 0;
     }
-    if (owner && p.move_counter) {
-        for (int o = 16; o > 0; o >>= 1) moves_done += __shfl_xor_sync(0xffffffffu, moves_done, o);
-        if (lane == 0 && moves_done) atomicAdd(p.move_counter, (unsigned long long)moves_done);
-    }
-    tc::tc_teardown(tmem_base);
-}
+};
 
 }  // namespace b2048
