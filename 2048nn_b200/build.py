@@ -25,7 +25,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    exp = [f"-D{d}" for d in os.environ.get("B2048_EXP", "").split(",") if d]
+    cmd = [nvcc] + NVCC_FLAGS + exp + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)  # the image's CC wrapper lacks some specs; use nvcc's default host gcc
     r = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], capture_output=True, text=True, env=env)

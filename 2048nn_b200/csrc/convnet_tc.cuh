@@ -183,6 +183,13 @@ __device__ __forceinline__ uint32_t act_off(int R, int c) { return (uint32_t)R *
 __device__ __forceinline__ int act_row(int x, int y, int b) { return (5 * x + 1 + y) * SLAB_ROWS + b; }
 
 
+// {lo, hi} -> packed fp16x2 with ReLU folded into the conversion (cvt.rn.relu.f16x2.f32: one instruction)
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -232,8 +239,10 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
     if ((threadIdx.x >> 5) == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ---- warp 0: weight producer ---------------------------------------------------------------------
-// Mirrors the MMA warp's control flow: per forward of a set, 7 layers x 3 chunks through the ring.
+// ---- producer warp: weights ---------------------------------------------------------------------
+// One "iteration" = one forward of every active set.  Each 24 KB chunk (layer, dy) is loaded ONCE per
+// iteration and consumed by both sets back to back, so the ring's two slots cover twice the MMA time.
+// Mirrors the MMA warp's control flow (same run flags, same chunk order).
 __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
@@ -243,34 +252,40 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) 
     uint32_t iter[NSETS];
     for (int i = 0; i < NSETS; i++) active[i] = true, iter[i] = 0;
     uint32_t prod = 0;
-    while (active[0] || active[1]) {
-        for (int l = 0; l < N_LAYERS; l++) {
-            for (int set = 0; set < NSETS; set++) {
-                if (!active[set]) continue;
-                if (l == 0) {  // the set's workers publish "run" before their first act_ready arrival
-                    mbar_wait(bars.act0 + 8 * set, (iter[set] * N_LAYERS) & 1);
-                    if (!s_run[8 * set]) {
-                        active[set] = false;
-                        continue;
-                    }
-                }
-                if (lane == 0) {
-                    for (int dyi = 0; dyi < 3; dyi++) {
-                        const uint32_t slot = prod % RING, use = prod / RING;
-                        if (use > 0) mbar_wait(bars.empty0 + 8 * slot, (use - 1) & 1);
-                        mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES);
-                        bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)(l * 3 + dyi) * CHUNK_BYTES,
-                                 CHUNK_BYTES, bars.full0 + 8 * slot);
-                        prod++;
-                    }
-                }
-                if (l == N_LAYERS - 1) iter[set]++;
+    for (;;) {
+        bool any = false;
+        for (int set = 0; set < NSETS; set++) {
+            if (!active[set]) continue;
+            // the set's workers publish "run" before their first act_ready arrival of the iteration
+            mbar_wait(bars.act0 + 8 * set, (iter[set] * N_LAYERS) & 1);
+            if (!s_run[8 * set]) active[set] = false;
+            else any = true, iter[set]++;
+        }
+        if (!any) break;
+        if (lane == 0) {
+            for (int c = 0; c < N_CHUNKS; c++) {
+                const uint32_t slot = prod % RING, use = prod / RING;
+                if (use > 0) mbar_wait(bars.empty0 + 8 * slot, (use - 1) & 1);
+#ifdef B2048_EXP_SMALL_W  // timing experiment only: load 1/6 of every chunk (wrong results)
+                mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES / 6);
+                bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES / 6,
+                         bars.full0 + 8 * slot);
+#else
+                mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES);
+                bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
+                         bars.full0 + 8 * slot);
+#endif
+                prod++;
             }
         }
+        prod = __shfl_sync(0xffffffffu, prod, 0);
     }
 }
 
-// ---- warp 1: MMA issuer -----------------------------------------------------------------------------
+// ---- MMA warp ------------------------------------------------------------------------------------------
+// Issue order per layer: chunk dy=-1 [set A, set B], dy=0 [A, B], dy=+1 [A, B].  A set's accumulators are
+// committed after its dy=+1 part, so its epilogue overlaps the other set's last third and the next layer's
+// first MMAs of the other set.
 __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
@@ -280,26 +295,37 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
     uint32_t phase[NSETS];
     for (int i = 0; i < NSETS; i++) active[i] = true, phase[i] = 0;
     uint32_t cons = 0;
-    while (active[0] || active[1]) {
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
+    for (;;) {
+        bool any = false;
         for (int l = 0; l < N_LAYERS; l++) {
-            for (int set = 0; set < NSETS; set++) {
-                if (!active[set]) continue;
-                mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
-                if (l == 0 && !s_run[8 * set]) {
-                    active[set] = false;
-                    continue;
-                }
-                tc_fence_after();
-                const uint32_t in_addr = sm_base + SM_ACT + set * ACT_BYTES;
-                const uint32_t acc_base = tmem_base + (uint32_t)(set * 256);
-                const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
-                for (int dyi = 0; dyi < 3; dyi++) {
-                    const uint32_t slot = cons % RING, use = cons / RING;
-                    mbar_wait(bars.full0 + 8 * slot, use & 1);
+            const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
+            for (int dyi = 0; dyi < 3; dyi++) {
+                uint32_t slot = 0;
+                bool have_chunk = false;
+                for (int set = 0; set < NSETS; set++) {
+                    if (!active[set]) continue;
+                    if (dyi == 0) {
+                        mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
+                        if (l == 0) {
+                            if (!s_run[8 * set]) {
+                                active[set] = false;
+                                continue;
+                            }
+                            any = true;
+                        }
+                    }
+                    if (!have_chunk) {
+                        slot = cons % RING;
+                        mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                        have_chunk = true;
+                    }
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t w_addr = sm_base + SM_RING + slot * CHUNK_BYTES;
-#pragma unroll 1
+                        const uint32_t in_lo = (sm_base + SM_ACT + set * ACT_BYTES) >> 4;
+                        const uint32_t w_lo = (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4;
+                        const uint32_t acc_base = tmem_base + (uint32_t)(set * 256);
+#pragma unroll
                         for (int si = 0; si < 4; si++) {
                             // slab order 0,3,1,2: the (dy=-1, k=0) MMAs of slabs 0 and 3 are the first writers of
                             // column blocks {0,1} and {2,3}: they overwrite, everything else accumulates.
@@ -308,23 +334,28 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
                             const int N = (x_hi - x_lo + 1) * 64;  // 128 at the borders, 192 inside
                             const int brow = (s == 0) ? 64 : 0;    // rows [dx=+1|dx=0|dx=-1]: no dx=+1 for s==0
                             const uint32_t idesc = make_idesc(128, N);
-                            const uint32_t a_addr = in_addr + (uint32_t)((5 * s + dyi) * SLAB_ROWS) * ROW_BYTES;
-                            const uint32_t b_addr = w_addr + (uint32_t)brow * ROW_BYTES;
+                            // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
+                            const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
+                            const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
                             const uint32_t d_addr = acc_base + (uint32_t)(x_lo * 64);
                             for (int k = 0; k < nk; k++) {
                                 const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
-                                umma_f16(d_addr, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, acc);
+                                umma_f16(d_addr, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                         acc);
                             }
                         }
-                        umma_commit(bars.empty0 + 8 * slot);  // ring slot reusable once these MMAs retire
+                        if (dyi == 2) umma_commit(bars.acc0 + 8 * set);
                     }
+                    __syncwarp();
+                    if (dyi == 2) phase[set]++;
+                }
+                if (have_chunk) {
+                    if (lane == 0) umma_commit(bars.empty0 + 8 * slot);  // slot reusable once these MMAs retire
                     __syncwarp();
                     cons++;
                 }
-                if (lane == 0) umma_commit(bars.acc0 + 8 * set);
-                __syncwarp();
-                phase[set]++;
             }
+            if (l == 0 && !any) return;
         }
     }
 }
@@ -335,62 +366,78 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
 //   ADD_RES  second conv of a block: add the block input kept in `res`
 //   KEEP_RES this output is a block input: remember it (packed fp16) in `res`
 //   LAST     last conv: do not write back; accumulate the 1x1 head conv on the fp32 values instead
-template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
-__device__ __forceinline__ void epilogue_layer(uint8_t *row0, uint8_t *row1, int sw, const float *bias, const float *tail,
-                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
-                                               float *dbg0) {
-    // register budget: res (64) dominates, so TMEM is drained 8 columns x 2 rows at a time
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG, int W>
+__device__ __forceinline__ void epilogue_layer_w(uint8_t *row0, uint8_t *row1, int sw, const float *bias,
+                                                 const float *tail, uint32_t acc0, uint32_t (&res)[2][32],
+                                                 float (&head_acc)[2][4], float *dbg0) {
+    // W = columns drained per tcgen05.ld (8 or 16), both rows loaded together, one wait::ld per step.
+    // Register budget: res (64) dominates; measured on B200: W=8 joint loads beat per-row pipelining.
 #pragma unroll
-    for (int c = 0; c < 8; c++) {  // 16-byte chunk = 8 channels
-        float v[2][8];
-        tmem_ld8(acc0 + (uint32_t)(c * 8), reinterpret_cast<uint32_t *>(v[0]));
-        tmem_ld8(acc0 + (uint32_t)(64 + c * 8), reinterpret_cast<uint32_t *>(v[1]));
-        const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8);
-        const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int cw = 0; cw < 64 / W; cw++) {
+        float v[2][W];
+        if (W == 8) {
+            tmem_ld8(acc0 + (uint32_t)(cw * W), reinterpret_cast<uint32_t *>(v[0]));
+            tmem_ld8(acc0 + (uint32_t)(64 + cw * W), reinterpret_cast<uint32_t *>(v[1]));
+        } else {
+            tmem_ld16(acc0 + (uint32_t)(cw * W), reinterpret_cast<uint32_t *>(v[0]));
+            tmem_ld16(acc0 + (uint32_t)(64 + cw * W), reinterpret_cast<uint32_t *>(v[1]));
+        }
         tmem_ld_wait();
 #pragma unroll
-        for (int xi = 0; xi < 2; xi++) {
-            uint4 pk;
-            uint32_t *pw = &pk.x;
+        for (int h = 0; h < W / 8; h++) {
+            const int c = cw * (W / 8) + h;  // 16-byte chunk = 8 channels
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                float a0 = v[xi][2 * jj] + bb[2 * jj];
-                float a1 = v[xi][2 * jj + 1] + bb[2 * jj + 1];
-                if (ADD_RES) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
-                    a0 += f.x, a1 += f.y;
+            for (int xi = 0; xi < 2; xi++) {
+                uint4 pk;
+                uint32_t *pw = &pk.x;
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    float a0 = v[xi][h * 8 + 2 * jj] + bb[2 * jj];
+                    float a1 = v[xi][h * 8 + 2 * jj + 1] + bb[2 * jj + 1];
+                    if (ADD_RES) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
+                        a0 += f.x, a1 += f.y;
+                    }
+                    if (LAST || DBG) v[xi][h * 8 + 2 * jj] = fmaxf(a0, 0.f), v[xi][h * 8 + 2 * jj + 1] = fmaxf(a1, 0.f);
+                    if (!LAST) {
+                        pw[jj] = pack_relu_f16x2(a0, a1);
+                        if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
+                    }
                 }
-                a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
-                if (LAST || DBG) v[xi][2 * jj] = a0, v[xi][2 * jj + 1] = a1;
-                if (!LAST) {
-                    const __half2 hh = __floats2half2_rn(a0, a1);
-                    pw[jj] = *reinterpret_cast<const uint32_t *>(&hh);
-                    if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
+                if (!LAST) *reinterpret_cast<uint4 *>((xi ? row1 : row0) + ((c ^ sw) << 4)) = pk;
+                if (DBG && dbg0) {
+#pragma unroll
+                    for (int co = 0; co < 8; co++) dbg0[((c * 8 + co) * 16) + xi] = v[xi][h * 8 + co];
                 }
-            }
-            if (!LAST) *reinterpret_cast<uint4 *>((xi ? row1 : row0) + ((c ^ sw) << 4)) = pk;
-            if (DBG && dbg0) {
+                if (LAST) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
 #pragma unroll
-                for (int co = 0; co < 8; co++) dbg0[((c * 8 + co) * 16) + xi] = v[xi][co];
-            }
-            if (LAST) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
-#pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    const float4 t0 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8);
-                    const float4 t1 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8 + 4);
-                    float sacc = head_acc[xi][c4];
-                    sacc = fmaf(v[xi][0], t0.x, sacc), sacc = fmaf(v[xi][1], t0.y, sacc);
-                    sacc = fmaf(v[xi][2], t0.z, sacc), sacc = fmaf(v[xi][3], t0.w, sacc);
-                    sacc = fmaf(v[xi][4], t1.x, sacc), sacc = fmaf(v[xi][5], t1.y, sacc);
-                    sacc = fmaf(v[xi][6], t1.z, sacc), sacc = fmaf(v[xi][7], t1.w, sacc);
-                    head_acc[xi][c4] = sacc;
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 t0 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8);
+                        const float4 t1 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8 + 4);
+                        float sacc = head_acc[xi][c4];
+                        sacc = fmaf(v[xi][h * 8 + 0], t0.x, sacc), sacc = fmaf(v[xi][h * 8 + 1], t0.y, sacc);
+                        sacc = fmaf(v[xi][h * 8 + 2], t0.z, sacc), sacc = fmaf(v[xi][h * 8 + 3], t0.w, sacc);
+                        sacc = fmaf(v[xi][h * 8 + 4], t1.x, sacc), sacc = fmaf(v[xi][h * 8 + 5], t1.y, sacc);
+                        sacc = fmaf(v[xi][h * 8 + 6], t1.z, sacc), sacc = fmaf(v[xi][h * 8 + 7], t1.w, sacc);
+                        head_acc[xi][c4] = sacc;
+                    }
                 }
             }
         }
     }
 }
-
+#ifndef B2048_EPI_W
+#define B2048_EPI_W 8
+#endif
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
+__device__ __forceinline__ void epilogue_layer(uint8_t *row0, uint8_t *row1, int sw, const float *bias, const float *tail,
+                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
+                                               float *dbg0) {
+    epilogue_layer_w<ADD_RES, KEEP_RES, LAST, DBG, B2048_EPI_W>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
+}
 
 // ---- worker groups -----------------------------------------------------------------------------------
 // Work policy (owner warp = first warp of a group, all 32 lanes call it):
