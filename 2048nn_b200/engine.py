@@ -179,28 +179,55 @@ def mcts_nn_lines(blob, precision, origins, number, seed, eval_id_base=0, line_b
 
 class HostPlayout:
     """Host-buffer front end of K2 for large batches: pinned host start boards in, pinned host
-    (final, score, moves) out, with the H2D / D2H copies enqueued on the same stream as the
-    kernel.  Buffers are allocated once and reused (what a caller streaming batches would do)."""
+    (score, moves[, final]) out.  The batch is cut into `chunks` pieces that flow through three streams
+    (H2D copy, kernel, D2H copy) so PCIe traffic hides behind the playouts.  Buffers are allocated once
+    and reused (what a caller streaming batches would do)."""
 
-    def __init__(self, n, device="cuda"):
+    def __init__(self, n, device="cuda", chunks=6, want_final=False):
         L.require_cuda()
         self.n = n
         self.device = torch.device(device)
+        self.want_final = want_final
+        self.chunks = max(1, min(chunks, n))
+        self.bounds = [(i * n // self.chunks, (i + 1) * n // self.chunks) for i in range(self.chunks)]
         self.d_start = torch.empty(n, dtype=torch.int64, device=self.device)
-        self.d_out = (torch.empty(n, dtype=torch.int64, device=self.device),
+        self.d_out = (torch.empty(n, dtype=torch.int64, device=self.device) if want_final else None,
                       torch.empty(n, dtype=torch.int32, device=self.device),
                       torch.empty(n, dtype=torch.int32, device=self.device))
-        self.h_out = (torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
-                      torch.empty(n, dtype=torch.int32).pin_memory())
+        self.h_out = (torch.empty(n, dtype=torch.int64).pin_memory() if want_final else None,
+                      torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory())
+        # two alternating kernel streams: the tail of chunk i (a few long games) overlaps the head of chunk i+1
+        self.s_in, self.s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.s_runs = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
         self.h2d_bytes = n * 8
-        self.d2h_bytes = n * 16
+        self.d2h_bytes = n * (16 if want_final else 8)
 
     def __call__(self, h_start, seed, gid_base=0, order=LUDR):
-        """h_start: pinned int64[n] host tensor of start boards (0 = fresh board).  Returns the
-        pinned host tensors (final, score, moves); synchronises the stream before returning."""
-        self.d_start.copy_(h_start, non_blocking=True)
-        playout_fixed(self.n, seed, gid_base, start=self.d_start, order=order, out=self.d_out)
-        for h, d in zip(self.h_out, self.d_out):
-            h.copy_(d, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        """h_start: pinned int64[n] host tensor of start boards (0 = fresh board).  Returns the pinned host
+        tensors (final or None, score, moves); the caller's stream waits for the result and the host is
+        synchronised before returning."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.s_in, self.s_out, *self.s_runs):
+            st.wait_stream(cur)
+        o = (C.c_uint8 * 4)(*[int(x) & 3 for x in order])
+        lib, ctx = L.load_library(), L.ctx(self.device)
+        for i, (b, e) in enumerate(self.bounds):
+            s_run = self.s_runs[i & 1]
+            with torch.cuda.stream(self.s_in):
+                self.d_start[b:e].copy_(h_start[b:e], non_blocking=True)
+                ev_in = self.s_in.record_event()
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                f = self.d_out[0][b:e] if self.want_final else None
+                L.check(lib.b2048_playout_fixed(ctx, L.ptr(self.d_start[b:e]), o, seed, gid_base + b, 0, L.ptr(f),
+                                                L.ptr(self.d_out[1][b:e]), L.ptr(self.d_out[2][b:e]), e - b,
+                                                C.c_void_p(s_run.cuda_stream)))
+                ev_run = s_run.record_event()
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_run)
+                for h, d in zip(self.h_out, self.d_out):
+                    if h is not None:
+                        h[b:e].copy_(d[b:e], non_blocking=True)
+        cur.wait_stream(self.s_out)
+        self.s_out.synchronize()
         return self.h_out

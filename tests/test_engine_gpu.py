@@ -174,3 +174,16 @@ def test_fixed_policy_distribution_ks(eng, orc):
     assert ks_2samp(gs, np.log10(rs.astype(np.float64) + 1)).pvalue > 1e-3
     assert ks_2samp(c.cpu().numpy().astype(np.float64), rc.astype(np.float64)).pvalue > 1e-3
     assert abs(gs.mean() - 3.3527) < 0.01
+
+
+def test_host_playout_pipeline_matches_device_path(eng, orc):
+    # host-buffer API (chunked H2D / kernel / D2H streams): same results as one device-resident launch
+    n = 50_000
+    start = eng.init_boards(n, 777, 0)
+    f, s, c = eng.playout_fixed(n, 9, 0, start=start)
+    hp = eng.HostPlayout(n, chunks=7, want_final=True)
+    hf, hs, hm = hp(start.cpu().pin_memory(), 9, 0)
+    assert torch.equal(hf, f.cpu()) and torch.equal(hs, s.cpu()) and torch.equal(hm, c.cpu())
+    hp2 = eng.HostPlayout(n, chunks=3)
+    _, hs2, hm2 = hp2(start.cpu().pin_memory(), 9, 0)
+    assert torch.equal(hs2, s.cpu()) and torch.equal(hm2, c.cpu())
