@@ -29,6 +29,7 @@ _SIGS = {
     "b2048_create": (C.c_int, [C.c_int, C.POINTER(P)]),
     "b2048_destroy": (C.c_int, [P]),
     "b2048_num_sms": (C.c_int, [P]),
+    "b2048_set_playout_variant": (C.c_int, [P, C.c_int]),
     "b2048_take_error_flag": (C.c_int, [P, P, C.POINTER(C.c_int)]),
     "b2048_tables": (C.c_int, [P, P, P, P, P, P, P]),
     "b2048_move_batch": (C.c_int, [P, P, P, C.c_int, P, P, P, i64, P]),

@@ -34,7 +34,9 @@ struct b2048_ctx {
     int num_sms;
     uint16_t *fin_fwd, *fin_rev;
     uint32_t *score;
-    uint8_t *moved_fwd, *moved_rev;
+    uint8_t *moved_fwd, *moved_rev, *legal;
+    uint2 *rowstat;
+    int k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide
     unsigned long long *counters;  // N_COUNTERS work cursors, one per in-flight launch
     int *err_flag;
     unsigned next_counter;
@@ -48,6 +50,8 @@ static Tables tables_of(const b2048_ctx *c) {
     t.fin_fwd = c->fin_fwd;
     t.fin_rev = c->fin_rev;
     t.score = c->score;
+    t.legal = c->legal;
+    t.rowstat = c->rowstat;
     return t;
 }
 
@@ -69,17 +73,22 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->score, 65536 * sizeof(uint32_t)));
     CK(cudaMalloc(&c->moved_fwd, 65536));
     CK(cudaMalloc(&c->moved_rev, 65536));
+    CK(cudaMalloc(&c->legal, 65536));
+    CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
+    c->k2_variant = 1;
     CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
     CK(cudaMemset(c->err_flag, 0, 2 * sizeof(int)));
     build_tables_kernel<<<65536 / 256, 256>>>(c->fin_fwd, c->fin_rev, c->score, c->moved_fwd, c->moved_rev,
-                                              c->err_flag + 1);
+                                              c->legal, c->rowstat, c->err_flag + 1);
     CK(cudaGetLastError());
     int mism = 0;
     CK(cudaMemcpy(&mism, c->err_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
     if (mism) return fail_msg("b2048_create: row-table invariants violated");
     CK(cudaFuncSetAttribute(playout_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    CK(cudaFuncSetAttribute(playout_fixed_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V2_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(playout_fixed_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V2_SMEM_BYTES));
     CK(cudaFuncSetAttribute(convnet_fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             CN_FP32_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -101,6 +110,8 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
     cudaFree(c->score);
     cudaFree(c->moved_fwd);
     cudaFree(c->moved_rev);
+    cudaFree(c->legal);
+    cudaFree(c->rowstat);
     cudaFree(c->counters);
     cudaFree(c->err_flag);
     cudaFree(c->rboard);
@@ -109,6 +120,12 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
 }
 
 extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
+
+extern "C" int b2048_set_playout_variant(b2048_ctx *c, int variant) {
+    if (variant != 0 && variant != 1) return fail_msg("b2048_set_playout_variant: variant must be 0 or 1");
+    c->k2_variant = variant;
+    return 0;
+}
 
 /* device error flag: set when a spawn hit countzero == 0 (ValueError in the reference).
  * Reads and clears it; synchronises `stream`. */
@@ -208,10 +225,16 @@ static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
     int grid = grid_for(p.n, 1024, c->num_sms);
     bool ludr = p.order[0] == 0 && p.order[1] == 1 && p.order[2] == 3 && p.order[3] == 2;
-    if (ludr)
+    if (c->k2_variant == 1) {
+        if (ludr)
+            playout_fixed_kernel2<true><<<grid, 1024, K2V2_SMEM_BYTES, st>>>(p);
+        else
+            playout_fixed_kernel2<false><<<grid, 1024, K2V2_SMEM_BYTES, st>>>(p);
+    } else if (ludr) {
         playout_fixed_kernel<true><<<grid, 1024, 131072, st>>>(p);
-    else
+    } else {
         playout_fixed_kernel<false><<<grid, 1024, 131072, st>>>(p);
+    }
     CK(cudaGetLastError());
     return 0;
 }

@@ -23,6 +23,8 @@ struct Tables {
     const uint16_t *fin_fwd;
     const uint16_t *fin_rev;
     const uint32_t *score;
+    const uint8_t *legal;  // u8[65536]: bit 0 = row moves toward nibble 0, bit 1 = toward nibble 3
+    const uint2 *rowstat;  // [65536] per row: .x = sum (t-1)*2^t ("potential"), .y = sum 2^t (tile sum)
 };
 
 // board.py:104-132 move_row restated for one thread (used only to BUILD the tables on device).
@@ -132,7 +134,17 @@ __device__ __forceinline__ u64 spawn_tile(u64 board, u64 draw, u32 &is_four) {
 }
 
 // generate_init_tiles (board.py:68-82) on the game's word stream (words 0..15 reserved).
+__device__ __forceinline__ u64 init_board_slow(u64 key);
 __device__ __forceinline__ u64 init_board(u64 key) {
+    // common case (15/16): pos1 != pos2 on the first try -> words 0..3 = two draws
+    const u64 d0 = rng_draw(key, 0), d1 = rng_draw(key, 1);
+    const u32 pos1 = __umulhi(hi32(d0), 16u), pos2 = __umulhi(lo32(d0), 16u);
+    if (pos1 == pos2) return init_board_slow(key);
+    const u64 t1 = 1ULL << (4 * pos1 + (__umulhi(hi32(d1), 10u) ? 0 : 1));
+    const u64 t2 = 1ULL << (4 * pos2 + (__umulhi(lo32(d1), 10u) ? 0 : 1));
+    return t1 | t2;
+}
+__device__ __noinline__ u64 init_board_slow(u64 key) {
     u32 w = 0;
     u32 pos1 = __umulhi(rng_word(key, w++), 16u);
     u32 pos2 = __umulhi(rng_word(key, w++), 16u);
@@ -190,6 +202,14 @@ __device__ __forceinline__ u32 potential(u64 b) {
         s += t ? ((t - 1u) << t) : 0u;
     }
     return s;
+}
+// potential and tile sum of a board from the per-row table (4 L2-resident loads instead of two
+// 16-step loops: this runs for a whole warp whenever one lane starts or finishes a game)
+__device__ __forceinline__ uint2 board_stat(u64 b, const Tables &tb) {
+    u32 lo = lo32(b), hi = hi32(b);
+    uint2 a = __ldg(tb.rowstat + (lo & 0xFFFFu)), c = __ldg(tb.rowstat + (lo >> 16));
+    uint2 d = __ldg(tb.rowstat + (hi & 0xFFFFu)), e = __ldg(tb.rowstat + (hi >> 16));
+    return make_uint2(a.x + c.x + d.x + e.x, a.y + c.y + d.y + e.y);
 }
 __device__ __forceinline__ u32 tile_sum(u64 b) {
     u32 s = 0;

@@ -9,7 +9,7 @@ namespace b2048 {
 // Table build on the device (replaces board.py:134-148).  One thread per row.
 // ---------------------------------------------------------------------------------------
 __global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score, uint8_t *moved_fwd,
-                                    uint8_t *moved_rev, int *mismatch) {
+                                    uint8_t *moved_rev, uint8_t *legal, uint2 *rowstat, int *mismatch) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= 65536) return;
     u32 ff, sf, fr, sr;
@@ -20,6 +20,8 @@ __global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32
     score[r] = sf;
     moved_fwd[r] = ff != r;
     moved_rev[r] = fr != r;
+    legal[r] = (uint8_t)((ff != r) | ((fr != r) << 1));
+    rowstat[r] = make_uint2(potential((u64)r), tile_sum((u64)r));
     // invariants the playout kernel relies on: equal scores, mirrored finals
     u32 mf, ms;
     row_slide(mirror32(r) & 0xFFFFu, false, mf, ms);
@@ -354,6 +356,167 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel(const PlayParams
             long r = slot / p.number;
             if (p.out_logsum) {
                 double t = log10((double)score + (double)rs + 1.0);  // mcts.py:31
+                long long q = __double2ll_rn(ldexp(t, 40));
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
+            }
+            if (p.out_count) atomicAdd(p.out_count + r, 1);
+            if (p.out_minmov) atomicMin(p.out_minmov + r, (int)count);
+        }
+        have = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 variant 2: legality first, then ONE uniform slide per move (no L,U,D,R attempt cascade).
+//
+// The cascade kernel above executes the Up/Down/Right attempts for a whole warp whenever any lane
+// needs them, with 27% / 7% / 2% of the lanes active (ncu: 14.8 of 32 threads per instruction).
+// Here every lane does the same work every step: 8 byte lookups in a 64 KB row-legality table (4 rows
+// of the board, 4 rows of its transpose) give the legal-move mask, the first legal direction of the
+// priority order is selected branch-free, and a single table slide is applied through
+// select / mirror / transpose steps that are predicated by the chosen direction.
+// Shared memory: 128 KB forward table + 64 KB legality table.
+// ---------------------------------------------------------------------------------------
+#define K2V2_SMEM_BYTES (131072 + 65536)
+#ifndef K2_REFILL_MIN
+#define K2_REFILL_MIN 3
+#endif
+
+template <bool LUDR>
+__global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParams p) {
+    extern __shared__ __align__(16) uint16_t sT[];
+    uint8_t *sL = reinterpret_cast<uint8_t *>(sT) + 131072;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tb.fin_fwd);
+        uint4 *dst = reinterpret_cast<uint4 *>(sT);
+        for (int i = threadIdx.x; i < 131072 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint4 *srcl = reinterpret_cast<const uint4 *>(p.tb.legal);
+        uint4 *dstl = reinterpret_cast<uint4 *>(sL);
+        for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) dstl[i] = __ldg(srcl + i);
+    }
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31;
+    const long total_threads = (long)gridDim.x * blockDim.x;
+    long item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // first game: static assignment
+    bool first = true, exhausted = false;
+    bool have = false;
+    u64 b = 0, key = 0;
+    u32 count = 0, n4 = 0, pot0 = 0, limit = 0, rs = 0;
+    long slot = 0;
+    const u32 o0 = p.order[0], o1 = p.order[1], o2 = p.order[2], o3 = p.order[3];
+
+    // All 32 lanes stay in the loop until the warp has no game left.  Starting a game costs a few
+    // hundred instructions for the whole warp, so dead lanes wait until K2_REFILL_MIN of them can
+    // be refilled together (ncu: per-lane refill left only 22 of 32 lanes active per instruction).
+    for (;;) {
+        unsigned alive_mask = __ballot_sync(0xffffffffu, have);
+        if (__popc(~alive_mask) >= K2_REFILL_MIN || alive_mask == 0u) {
+            if (!have && !exhausted) {
+                if (!first) {
+                    unsigned m = __activemask();
+                    int leader = __ffs(m) - 1;
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    item = total_threads + (long)base + __popc(m & ((1u << lane) - 1));
+                }
+                first = false;
+                if (item >= p.n) {
+                    exhausted = true;
+                } else {
+                    slot = item;
+                    count = 0;
+                    n4 = 0;
+                    rs = 0;
+                    bool skip = false;
+                    if (p.root_mode) {
+                        long r = item / p.line_count;
+                        int j = p.line_begin + (int)(item - r * p.line_count);
+                        slot = r * p.number + j;
+                        if (!p.rlegal[r]) {
+                            skip = true;
+                        } else {
+                            key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
+                            u64 rb = p.rboard[r];
+                            rs = p.rscore[r];
+                            if (countzero(rb) == 0) {
+                                *p.err_flag = 1;
+                                skip = true;
+                            } else {
+                                u32 four;
+                                b = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);
+                            }
+                        }
+                    } else {
+                        key = rng_key(p.seed, p.gid_base + (u64)item);
+                        u64 s0 = p.start ? p.start[item] : 0ULL;
+                        b = s0 ? s0 : init_board(key);
+                    }
+                    if (skip) {
+                        if (p.out_final) p.out_final[slot] = 0;
+                        if (p.out_score) p.out_score[slot] = 0;
+                        if (p.out_moves) p.out_moves[slot] = 0;
+                    } else {
+                        const uint2 st = board_stat(b, p.tb);
+                        pot0 = st.x;
+                        limit = st.y >= 65536u ? 0u : ((65536u - st.y + 3u) >> 2);  // moves that cannot annihilate
+                        have = true;
+                    }
+                }
+            }
+            alive_mask = __ballot_sync(0xffffffffu, have);
+            if (alive_mask == 0u && __all_sync(0xffffffffu, exhausted)) break;
+        }
+        if (!have) continue;
+
+        // ---- legality of all four directions ---------------------------------------------------------
+        const u64 bt = transpose(b);
+        const u32 lo = lo32(b), hi = hi32(b), tlo = lo32(bt), thi = hi32(bt);
+        const u32 hm = sL[lo & 0xFFFFu] | sL[lo >> 16] | sL[hi & 0xFFFFu] | sL[hi >> 16];      // bit0 L, bit1 R
+        const u32 vm = sL[tlo & 0xFFFFu] | sL[tlo >> 16] | sL[thi & 0xFFFFu] | sL[thi >> 16];  // bit0 U, bit1 D
+        const bool alive = (hm | vm) != 0;
+        if (alive && count < limit) {
+            u32 d;
+            if (LUDR) {
+                d = (hm & 1u) ? 0u : (vm & 1u) ? 1u : (vm & 2u) ? 3u : 2u;
+            } else {
+                const u32 mask = (hm & 1u) | ((vm & 1u) << 1) | ((hm & 2u) << 1) | ((vm & 2u) << 2);
+                d = ((mask >> o0) & 1u) ? o0 : ((mask >> o1) & 1u) ? o1 : ((mask >> o2) & 1u) ? o2 : o3;
+            }
+            // ---- one slide, direction folded into data movement ------------------------------------
+            u64 x = (d & 1u) ? bt : b;
+            const bool rev = (d & 2u) != 0;
+            u64 xm = mirror(x);
+            x = rev ? xm : x;
+            u64 y = slide_left(x, sT);
+            u64 ym = mirror(y);
+            y = rev ? ym : y;
+            u64 yt = transpose(y);
+            y = (d & 1u) ? yt : y;
+            u32 four;
+            b = spawn_tile(y, rng_draw(key, B2048_INIT_DRAWS + p.spawn0 + count), four);
+            n4 += four;
+            count++;
+            continue;
+        }
+
+        // ---- game over (or hand-over to the exact path) ----------------------------------------------
+        u32 score = board_stat(b, p.tb).x - pot0 - 4u * n4;
+        if (alive) {
+            ExactResult r = finish_exact(p, b, key, count, score);
+            b = r.b;
+            count = r.count;
+            score = r.score;
+            if (r.err) *p.err_flag = 1;
+        }
+        if (p.out_final) p.out_final[slot] = b;
+        if (p.out_score) p.out_score[slot] = score;
+        if (p.out_moves) p.out_moves[slot] = count;
+        if (p.root_mode) {
+            long r = slot / p.number;
+            if (p.out_logsum) {
+                double t = log10((double)score + (double)rs + 1.0);
                 long long q = __double2ll_rn(ldexp(t, 40));
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
             }

@@ -231,3 +231,8 @@ class HostPlayout:
         cur.wait_stream(self.s_out)
         self.s_out.synchronize()
         return self.h_out
+
+
+def set_playout_variant(variant, device=None):
+    """K2 kernel variant: 1 (default) legality-first uniform slide, 0 the L,U,D,R attempt cascade."""
+    L.check(L.load_library().b2048_set_playout_variant(L.ctx(device), int(variant)))

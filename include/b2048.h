@@ -58,6 +58,10 @@ int b2048_create(int device, b2048_ctx **out);
 int b2048_destroy(b2048_ctx *ctx);
 int b2048_num_sms(const b2048_ctx *ctx);
 
+/* Fixed-order playout kernel variant: 1 (default) = legality-first with one uniform table slide per
+ * move; 0 = the L,U,D,R attempt cascade.  Both are bit-exact; the switch exists for A/B measurements. */
+int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
+
 /* Device error flag: set when a spawn met countzero == 0 (the reference raises ValueError from
  * randrange(0), board.py:87).  Reads and clears it into *out_host; synchronises `stream`. */
 int b2048_take_error_flag(b2048_ctx *ctx, void *stream, int *out_host);

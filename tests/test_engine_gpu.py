@@ -187,3 +187,20 @@ def test_host_playout_pipeline_matches_device_path(eng, orc):
     hp2 = eng.HostPlayout(n, chunks=3)
     _, hs2, hm2 = hp2(start.cpu().pin_memory(), 9, 0)
     assert torch.equal(hs2, s.cpu()) and torch.equal(hm2, c.cpu())
+
+
+def test_both_playout_variants_are_bit_exact(eng, orc, eg):
+    n = eg["pf_final"].size
+    try:
+        for variant in (0, 1):
+            eng.set_playout_variant(variant)
+            f, s, c = eng.playout_fixed(n, int(eg["pf_seed"]), 0)
+            assert np.array_equal(host_u64(f), eg["pf_final"]) and np.array_equal(s.cpu().numpy().astype(np.uint64), eg["pf_score"])
+            assert np.array_equal(c.cpu().numpy().astype(np.uint64), eg["pf_count"])
+            f, s, c = eng.playout_fixed(50_000, 5, 123, order=(3, 0, 2, 1))
+            keys = [orc.rng_key(5, 123 + g) for g in range(300)]
+            for g in range(300):
+                w = orc.play_order(0, (3, 0, 2, 1), keys[g])
+                assert (int(host_u64(f)[g]), int(s[g].item()), int(c[g].item())) == w
+    finally:
+        eng.set_playout_variant(1)
