@@ -436,3 +436,11 @@ extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, cons
     p.move_counter = (unsigned long long *)move_counter;
     return launch_nn(c, precision, p, st);
 }
+
+#ifdef B2048_TRACE
+extern "C" int b2048_debug_trace(long long *out_host, int n) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out_host, tc::g_trace, sizeof(long long) * (n < 512 ? n : 512)));
+    return 0;
+}
+#endif

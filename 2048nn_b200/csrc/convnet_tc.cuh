@@ -57,7 +57,7 @@ constexpr int PRODUCER_WARP = WORKER_WARPS;       // warp 16
 constexpr int MMA_WARP = WORKER_WARPS + 1;        // warp 17 (18, 19 idle: whole warpgroup for setmaxnreg)
 constexpr int NUM_WARPS = WORKER_WARPS + 4;
 constexpr int NUM_THREADS = NUM_WARPS * 32;       // 640
-constexpr int WORKER_REGS = 112, CONTROL_REGS = 32;  // setmaxnreg pool = launch allocation 640 x 96: 16*32*112 + 4*32*32 = 61,440
+constexpr int WORKER_REGS = 104, CONTROL_REGS = 56;  // setmaxnreg pool = launch allocation 640 x 96 = 61,440 >= 16*32*104 + 4*32*56
 constexpr int TMEM_COLS = 512;
 
 // blob: [21 chunks fp16, pre-swizzled] [fp32 tail: bias 7x64 | w7 4x64 | b7 4 | fcw 4x64 | fcb 4]
@@ -75,7 +75,8 @@ constexpr int SM_LOGITS = SM_BOARDS + NSETS * 32 * 8;      // NSETS x 32 x 4 f32
 constexpr int SM_RUN = SM_LOGITS + NSETS * 32 * 16;        // NSETS x {run flag, debug base}
 constexpr int SM_BARS = SM_RUN + 32 * NSETS;                      // mbarriers: full[RING] empty[RING] acc[NSETS] act[NSETS]
 constexpr int SM_TMEMPTR = SM_BARS + 8 * (2 * RING + 2 * NSETS);
-constexpr int SM_TOTAL = SM_TMEMPTR + 16;
+constexpr int SM_CAND = SM_TMEMPTR + 16;                   // NSETS x 32 slots x 64 B: work-policy scratch (candidate moves)
+constexpr int SM_TOTAL = SM_CAND + NSETS * 32 * 64;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
 
 constexpr int HEAD_STRIDE = 65;  // floats per board in the head staging area (bank-conflict padding)
@@ -105,6 +106,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// non-blocking probe: true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -132,6 +147,30 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, executed by ALL lanes of the (converged) MMA warp with warp-uniform operands; one elected lane
+// issues.  Keeping the descriptor arithmetic warp-uniform lets ptxas hold the operands in uniform registers
+// instead of a per-MMA R2UR/ELECT waterfall (measured: the issue path, not the tensor pipe, set the pace).
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -190,6 +229,16 @@ __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
     return d;
 }
 
+#ifdef B2048_TRACE  // bring-up instrumentation: clock64 timeline of CTA 0 (iteration B2048_TRACE of each set)
+__device__ long long g_trace[512];
+#define TC_TRACE(iter, idx)                                                                  \
+    do {                                                                                     \
+        if (blockIdx.x == 0 && (iter) == B2048_TRACE && (threadIdx.x & 31) == 0) g_trace[idx] = clock64(); \
+    } while (0)
+#else
+#define TC_TRACE(iter, idx) do { } while (0)
+#endif
+
 __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -231,6 +280,7 @@ __device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *b
     __syncthreads();
     tc_fence_after();
     tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_TMEMPTR);
+    if (tmem_base != 0) __trap();  // the CTA allocates all 512 columns, so the allocation starts at lane 0 / column 0
     return sm;
 }
 __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
@@ -286,6 +336,33 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) 
 // Issue order per layer: chunk dy=-1 [set A, set B], dy=0 [A, B], dy=+1 [A, B].  A set's accumulators are
 // committed after its dy=+1 part, so its epilogue overlaps the other set's last third and the next layer's
 // first MMAs of the other set.
+//
+// Measured on B200 (tools/tc_trace.py): one tcgen05.mma M=128 K=16 from shared memory retires every
+// ~125 cycles whether N is 128 or 192: the 128-row A fetch from shared memory paces it (a 128 x 256 tile
+// would be balanced), so this formulation tops out near 64% of the tensor peak.  Taking the next unit's
+// barrier waits in the middle of an MMA burst was tried and changed nothing: the issue side is not the limit.
+__device__ __forceinline__ void issue_slabs(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi,
+                                            int nk, int si_begin, int si_end) {
+#pragma unroll
+    for (int si = si_begin; si < si_end; si++) {
+        // slab order 0,3,1,2: the (dy=-1, k=0) MMAs of slabs 0 and 3 are the first writers of column blocks
+        // {0,1} and {2,3}: they overwrite, everything else accumulates.
+        const int s = (si == 0) ? 0 : (si == 1) ? 3 : si - 1;
+        const int x_lo = s > 0 ? s - 1 : 0, x_hi = s < 3 ? s + 1 : 3;
+        const int N = (x_hi - x_lo + 1) * 64;  // 128 at the borders, 192 inside
+        const int brow = (s == 0) ? 64 : 0;    // rows [dx=+1|dx=0|dx=-1]: no dx=+1 for s==0
+        const uint32_t idesc = make_idesc(128, N);
+        // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
+        const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
+        const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
+        const uint32_t d_addr = acc_base + (uint32_t)(x_lo * 64);
+        for (int k = 0; k < nk; k++) {
+            const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
+            umma_f16_elect(d_addr, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, acc);
+        }
+    }
+}
+
 __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
@@ -296,17 +373,20 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
     for (int i = 0; i < NSETS; i++) active[i] = true, phase[i] = 0;
     uint32_t cons = 0;
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
+    int trace_iter = -1;
     for (;;) {
         bool any = false;
+        trace_iter++;
         for (int l = 0; l < N_LAYERS; l++) {
             const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
             for (int dyi = 0; dyi < 3; dyi++) {
-                uint32_t slot = 0;
+                const uint32_t slot = cons % RING;
                 bool have_chunk = false;
                 for (int set = 0; set < NSETS; set++) {
                     if (!active[set]) continue;
                     if (dyi == 0) {
                         mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
+                        TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
                         if (l == 0) {
                             if (!s_run[8 * set]) {
                                 active[set] = false;
@@ -316,42 +396,20 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
                         }
                     }
                     if (!have_chunk) {
-                        slot = cons % RING;
                         mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                        TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
                         have_chunk = true;
                     }
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t in_lo = (sm_base + SM_ACT + set * ACT_BYTES) >> 4;
-                        const uint32_t w_lo = (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4;
-                        const uint32_t acc_base = tmem_base + (uint32_t)(set * 256);
-#pragma unroll
-                        for (int si = 0; si < 4; si++) {
-                            // slab order 0,3,1,2: the (dy=-1, k=0) MMAs of slabs 0 and 3 are the first writers of
-                            // column blocks {0,1} and {2,3}: they overwrite, everything else accumulates.
-                            const int s = (si == 0) ? 0 : (si == 1) ? 3 : si - 1;
-                            const int x_lo = s > 0 ? s - 1 : 0, x_hi = s < 3 ? s + 1 : 3;
-                            const int N = (x_hi - x_lo + 1) * 64;  // 128 at the borders, 192 inside
-                            const int brow = (s == 0) ? 64 : 0;    // rows [dx=+1|dx=0|dx=-1]: no dx=+1 for s==0
-                            const uint32_t idesc = make_idesc(128, N);
-                            // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
-                            const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
-                            const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
-                            const uint32_t d_addr = acc_base + (uint32_t)(x_lo * 64);
-                            for (int k = 0; k < nk; k++) {
-                                const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
-                                umma_f16(d_addr, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
-                                         acc);
-                            }
-                        }
-                        if (dyi == 2) umma_commit(bars.acc0 + 8 * set);
-                    }
-                    __syncwarp();
+                    // whole warp, uniform operands; one elected lane issues.  tmem_base is 0: the CTA owns all 512 columns
+                    issue_slabs((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                                (uint32_t)(set * 256), desc_hi, dyi, nk, 0, 4);
+                    if (dyi == 2) umma_commit_elect(bars.acc0 + 8 * set);
+                    if (dyi == 2) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
                     if (dyi == 2) phase[set]++;
                 }
                 if (have_chunk) {
-                    if (lane == 0) umma_commit(bars.empty0 + 8 * slot);  // slot reusable once these MMAs retire
-                    __syncwarp();
+                    umma_commit_elect(bars.empty0 + 8 * slot);  // slot reusable once these MMAs retire
                     cons++;
                 }
             }
@@ -446,7 +504,10 @@ __device__ __forceinline__ void epilogue_layer(uint8_t *row0, uint8_t *row1, int
 //     // consume the previous forward's outputs (unless first), then provide the next 32 boards.
 //     // returns false when the set is finished.
 //     static bool step(const Params&, State&, bool first, const float *logits, unsigned long long *boards,
-//                      int lane, long &dbg_base); };
+//                      int lane, long &dbg_base, uint8_t *scratch);
+//     // called right after the boards are published: start long-latency work for the NEXT step() so that it
+//     // overlaps the forward (scratch = 64 B of shared memory per slot)
+//     static void prefetch(const Params&, State&, uint8_t *scratch, int lane); };
 template <class Work, bool DBG>
 __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, const typename Work::Params &wp, int set,
                                             int j, float *dbg, int dbg_layer, long dbg_n) {
@@ -473,10 +534,12 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
     uint32_t phase = 0;
     bool first = true;
     uint32_t res[2][32];  // residual input of the current block, packed fp16
+    int trace_iter = -1;
     for (;;) {
+        trace_iter++;
         if (j == 0) {
             long db = 0;
-            bool run = Work::step(wp, ws, first, s_logits, s_boards, lane, db);
+            bool run = Work::step(wp, ws, first, s_logits, s_boards, lane, db, sm + SM_CAND + set * 2048);
             if (lane == 0) {
                 *s_run = run ? 1 : 0;
                 *s_dbgbase = db;
@@ -489,6 +552,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             if (lane == 0) mbar_arrive(bar_act);  // tells the MMA / producer warps that this set is done
             break;
         }
+        if (j == 0) Work::prefetch(wp, ws, sm + SM_CAND + set * 2048, lane);
         // ---- encode: one-hot rows (channels [0,16) and again [16,32) for the hi/lo weight split) --------
         {
             const unsigned long long brd = s_boards[lane];
@@ -522,6 +586,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
         for (int l = 0; l < N_LAYERS; l++) {
             const float *bias = tail + TAIL_BIAS + l * 64;
             mbar_wait(bar_acc, phase & 1);
+            if (j == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 2);
             tc_fence_after();
             if (DBG) {
                 const long gb = *s_dbgbase + lane;
@@ -541,6 +606,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
             }
+            if (j == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 3);
             phase++;
         }
         // ---- head: stage [board][c4*16 + pos] in the image's first data slab, FC by the owner warp --------
@@ -602,8 +668,9 @@ struct FwdWork {
         long base;
     };
     __device__ static void init(State &st) { st.base = -1; }
+    __device__ static void prefetch(const Params &, State &, uint8_t *, int) {}
     __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
-                                int lane, long &dbg_base) {
+                                int lane, long &dbg_base, uint8_t *) {
         if (!first && st.base + lane < p.n) {
             const float4 z = reinterpret_cast<const float4 *>(logits)[lane];
             if (p.out_logits) reinterpret_cast<float4 *>(p.out_logits)[st.base + lane] = z;

@@ -137,6 +137,53 @@ __device__ __forceinline__ void nn_move(const NNPlayParams &p, GameSlot &g, cons
     if (!moved) nn_finish(p, g);
 }
 
+// Candidate moves of a slot, computed while the network runs (PlayWork::prefetch) so that the move choice
+// after the forward is pure ALU work: the four moved boards, their merge scores and the group's current
+// minimum (slightly stale is fine: a larger bound only delays the early stop, the minimum is unaffected).
+struct SlotCand {
+    u64 board[4];
+    u32 score[4];
+    int gmin;
+    u32 pad[3];
+};
+static_assert(sizeof(SlotCand) == 64, "SlotCand must be 64 bytes");
+
+__device__ __forceinline__ void nn_move_cand(const NNPlayParams &p, GameSlot &g, const float *z, const SlotCand &c,
+                                             u32 &moves_done) {
+    if (g.group >= 0 && (int)g.count >= c.gmin) {
+        nn_finish(p, g);
+        return;
+    }
+    // rank of each direction in descending logit order (stable: ties -> lower index first)
+    float zz[4] = {z[0], z[1], z[2], z[3]};
+    int best = -1;
+    float bz = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const bool legal = c.board[d] != g.board;
+        if (legal && (best < 0 || zz[d] > bz)) best = d, bz = zz[d];
+    }
+    if (best < 0) {
+        nn_finish(p, g);
+        return;
+    }
+    u64 f = c.board[0];
+    u32 s = c.score[0];
+#pragma unroll
+    for (int d = 1; d < 4; d++)
+        if (best == d) f = c.board[d], s = c.score[d];
+    if (countzero(f) == 0) {
+        *p.err_flag = 1;
+        nn_finish(p, g);
+        return;
+    }
+    u32 four;
+    g.board = spawn_tile(f, rng_draw(g.key, B2048_INIT_DRAWS + p.spawn0 + g.count), four);
+    g.score += s;
+    g.count++;
+    moves_done++;
+}
+
 // Exact-mode kernel: 8 game slots per CTA, fp32 CUDA-core forward.
 __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -183,10 +230,22 @@ struct PlayWork {
         st.moves_done = 0;
         st.queue_empty = false;
     }
+    __device__ static void prefetch(const Params &p, State &st, uint8_t *scratch, int lane) {
+        if (!st.g.live) return;
+        SlotCand *c = reinterpret_cast<SlotCand *>(scratch) + lane;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            u32 s;
+            c->board[d] = move_exact(st.g.board, d, p.tb, s);
+            c->score[d] = s;
+        }
+        c->gmin = (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff;
+    }
     __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
-                                int lane, long &dbg_base) {
+                                int lane, long &dbg_base, uint8_t *scratch) {
         dbg_base = 0;
-        if (!first && st.g.live) nn_move(p, st.g, logits + 4 * lane, st.moves_done);
+        if (!first && st.g.live)
+            nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
         if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
         s_boards[lane] = st.g.live ? st.g.board : 0ULL;
         const unsigned any = __ballot_sync(0xffffffffu, st.g.live);
