@@ -54,7 +54,7 @@ constexpr int NSETS = 2;                          // tile-sets in flight per CTA
 constexpr int GROUP_WARPS = 8;                    // worker warps per tile-set
 constexpr int WORKER_WARPS = NSETS * GROUP_WARPS;  // warps 0..15
 constexpr int PRODUCER_WARP = WORKER_WARPS;       // warp 16
-constexpr int MMA_WARP = WORKER_WARPS + 1;        // warp 17 (18, 19 idle: whole warpgroup for setmaxnreg)
+constexpr int MMA_WARP = WORKER_WARPS + 1;        // warps 17, 18: MMA issuers of accumulator halves 0 / 1 (19 idle)
 constexpr int NUM_WARPS = WORKER_WARPS + 4;
 constexpr int NUM_THREADS = NUM_WARPS * 32;       // 640
 constexpr int WORKER_REGS = 104, CONTROL_REGS = 56;  // setmaxnreg pool = launch allocation 640 x 96 = 61,440 >= 16*32*104 + 4*32*56
@@ -266,10 +266,10 @@ __device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *b
         Bars b(sm_base);
         for (int i = 0; i < RING; i++) {
             mbar_init(b.full0 + 8 * i, 1);
-            mbar_init(b.empty0 + 8 * i, 1);
+            mbar_init(b.empty0 + 8 * i, 2);  // one arrival per MMA-issuing warp
         }
         for (int i = 0; i < NSETS; i++) {
-            mbar_init(b.acc0 + 8 * i, 1);            // tcgen05.commit
+            mbar_init(b.acc0 + 8 * i, 2);            // tcgen05.commit of the two MMA-issuing warps
             mbar_init(b.act0 + 8 * i, GROUP_WARPS);  // one arrival per worker warp of the set
         }
         fence_mbar_init();
@@ -332,42 +332,44 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) 
     }
 }
 
-// ---- MMA warp ------------------------------------------------------------------------------------------
-// Issue order per layer: chunk dy=-1 [set A, set B], dy=0 [A, B], dy=+1 [A, B].  A set's accumulators are
+// ---- MMA warps -----------------------------------------------------------------------------------------
+// Unit order per layer: chunk dy=-1 [set A, set B], dy=0 [A, B], dy=+1 [A, B].  A set's accumulators are
 // committed after its dy=+1 part, so its epilogue overlaps the other set's last third and the next layer's
-// first MMAs of the other set.
+// first MMAs of the other set (ping-pong).
 //
-// Measured on B200 (tools/tc_trace.py): one tcgen05.mma M=128 K=16 from shared memory retires every
-// ~125 cycles whether N is 128 or 192: the 128-row A fetch from shared memory paces it (a 128 x 256 tile
-// would be balanced), so this formulation tops out near 64% of the tensor peak.  Taking the next unit's
-// barrier waits in the middle of an MMA burst was tried and changed nothing: the issue side is not the limit.
-__device__ __forceinline__ void issue_slabs(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi,
-                                            int nk, int si_begin, int si_end) {
+// Measured on B200 (tools/tc_trace.py): a single thread needs ~100-125 cycles per tcgen05.mma (descriptor
+// arithmetic, R2UR moves, election), more than the tensor pipe needs for N <= 192 (64-96 cycles).  The
+// issue work of every unit is therefore split over TWO warps that own disjoint halves of the accumulator:
+//   half 0 -> output column blocks {0,1}:  slab 0 (N=128), slab 1 (N=128), slab 2 (N=64: block 1 only)
+//   half 1 -> output column blocks {2,3}:  slab 3 (N=128), slab 2 (N=128), slab 1 (N=64: block 2 only)
+// Same tensor work as one N=128/192/192/128 sweep, each half's first MMA (dy=-1, k=0) is its own first
+// writer (overwrite), and no ordering between the two issuers is needed.
+__device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi,
+                                           int nk, int half) {
 #pragma unroll
-    for (int si = si_begin; si < si_end; si++) {
-        // slab order 0,3,1,2: the (dy=-1, k=0) MMAs of slabs 0 and 3 are the first writers of column blocks
-        // {0,1} and {2,3}: they overwrite, everything else accumulates.
-        const int s = (si == 0) ? 0 : (si == 1) ? 3 : si - 1;
-        const int x_lo = s > 0 ? s - 1 : 0, x_hi = s < 3 ? s + 1 : 3;
-        const int N = (x_hi - x_lo + 1) * 64;  // 128 at the borders, 192 inside
-        const int brow = (s == 0) ? 64 : 0;    // rows [dx=+1|dx=0|dx=-1]: no dx=+1 for s==0
+    for (int i = 0; i < 3; i++) {
+        // (slab, first B row, N, first D column) of this half's i-th MMA group; chunk rows are
+        // [dx=+1 -> x=s-1 | dx=0 -> x=s | dx=-1 -> x=s+1] x 64
+        const int s = half == 0 ? i : 3 - i;
+        const int brow = half == 0 ? (i == 0 ? 64 : 0) : (i == 0 ? 0 : (i == 1 ? 64 : 128));
+        const int N = (i == 2) ? 64 : 128;
+        const int dcol = half == 0 ? (i == 2 ? 64 : 0) : 128;
         const uint32_t idesc = make_idesc(128, N);
         // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
         const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
         const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
-        const uint32_t d_addr = acc_base + (uint32_t)(x_lo * 64);
+        const uint32_t d_addr = acc_base + (uint32_t)dcol;
         for (int k = 0; k < nk; k++) {
-            const uint32_t acc = (dyi == 0 && k == 0 && si < 2) ? 0u : 1u;
+            const uint32_t acc = (dyi == 0 && k == 0 && i == 0) ? 0u : 1u;
             umma_f16_elect(d_addr, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, acc);
         }
     }
 }
 
-__device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
+__device__ __forceinline__ void mma_loop(uint8_t *sm, int half) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
     const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
-    const int lane = threadIdx.x & 31;
     bool active[NSETS];
     uint32_t phase[NSETS];
     for (int i = 0; i < NSETS; i++) active[i] = true, phase[i] = 0;
@@ -386,7 +388,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
                     if (!active[set]) continue;
                     if (dyi == 0) {
                         mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
-                        TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
+                        if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
                         if (l == 0) {
                             if (!s_run[8 * set]) {
                                 active[set] = false;
@@ -397,19 +399,19 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, uint32_t tmem_base) {
                     }
                     if (!have_chunk) {
                         mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
-                        TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
+                        if (half == 0) TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
                         have_chunk = true;
                     }
                     tc_fence_after();
-                    // whole warp, uniform operands; one elected lane issues.  tmem_base is 0: the CTA owns all 512 columns
-                    issue_slabs((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                                (uint32_t)(set * 256), desc_hi, dyi, nk, 0, 4);
-                    if (dyi == 2) umma_commit_elect(bars.acc0 + 8 * set);
-                    if (dyi == 2) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
+                    // whole warp, uniform operands, one elected lane issues; tmem_base is 0 (all 512 columns owned)
+                    issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                               (uint32_t)(set * 256), desc_hi, dyi, nk, half);
+                    if (dyi == 2) umma_commit_elect(bars.acc0 + 8 * set);  // this half of the set's accumulators
+                    if (dyi == 2 && half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
                     if (dyi == 2) phase[set]++;
                 }
                 if (have_chunk) {
-                    umma_commit_elect(bars.empty0 + 8 * slot);  // slot reusable once these MMAs retire
+                    umma_commit_elect(bars.empty0 + 8 * slot);  // this half's "slot reusable"
                     cons++;
                 }
             }
@@ -650,7 +652,7 @@ tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float 
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
         if (warp == PRODUCER_WARP) producer_loop(sm, blob);
-        else if (warp == MMA_WARP) mma_loop(sm, tmem_base);
+        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop(sm, warp - MMA_WARP);
     }
     tc_teardown(tmem_base);
 }
