@@ -24,3 +24,8 @@ tt = np.array(buf[:], dtype=np.int64)[256:320].reshape(2, 32)[:, :16]
 for s in range(2):
     d = np.diff(tt[s])
     print(f"set{s} L3 dy1 per-MMA issue intervals (slab order 0,3,1,2; N=128,128,192,192):", d.tolist(), "first-last", int(tt[s][-1] - tt[s][0]))
+e = np.array(buf[:], dtype=np.int64)[384:384 + 56].reshape(14, 4)
+for l in range(1, 6):
+    for s_ in range(2):
+        r = t[l * 2 + s_]; x = e[l * 2 + s_]
+        print(f"L{l} set{s_}: acc_ready->chunks_done {int(x[0]-r[2])}  tc_fence_before {int(x[1]-x[0])}  fence.proxy.async {int(x[2]-x[1])}  arrive {int(r[3]-x[2])}")
