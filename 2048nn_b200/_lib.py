@@ -37,6 +37,8 @@ _SIGS = {
     "b2048_init_boards": (C.c_int, [P, u64, u64, P, i64, P]),
     "b2048_spawn_batch": (C.c_int, [P, P, u64, P, u64, P, u32, P, P, i64, P]),
     "b2048_policy_step": (C.c_int, [P, P, P, u64, P, u64, P, P, P, P, i64, P]),
+    "b2048_encode_boards": (C.c_int, [P, P, C.c_int, P, i64, P]),
+    "b2048_soft_targets": (C.c_int, [P, P, C.c_float, P, i64, P]),
     "b2048_rng_draws": (C.c_int, [P, u64, u64, u64, C.c_int, P, i64, P]),
     "b2048_playout_fixed": (C.c_int, [P, P, P, u64, u64, u32, P, P, P, i64, P]),
     "b2048_convnet_blob_bytes": (i64, [C.c_int]),

@@ -216,6 +216,24 @@ extern "C" int b2048_policy_step(b2048_ctx *c, const uint64_t *boards, const uin
     return 0;
 }
 
+extern "C" int b2048_encode_boards(b2048_ctx *c, const uint64_t *boards, int mode, float *out, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    if (mode != 0 && mode != 1) return fail_msg("b2048_encode_boards: mode must be 0 (exponents) or 1 (one-hot)");
+    const long total = (long)n * (mode ? 64 : 4);
+    encode_boards_kernel<<<grid_for(total, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+        (const u64 *)boards, mode, reinterpret_cast<float4 *>(out), (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_soft_targets(b2048_ctx *c, const float *results, float soft, float *out, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    soft_targets_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(results), soft, reinterpret_cast<float4 *>(out), (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st);
 static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     p.tb = tables_of(c);

@@ -136,6 +136,56 @@ __global__ void policy_step_kernel(Tables tb, const u64 *__restrict__ boards, co
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Training-record side of the path: board encodings and soft targets of
+// game_dataset.py:6-48.  Pure HBM streaming: 8 B in, 64 B (exponents) or 1,024 B (one-hot) out per board.
+// ---------------------------------------------------------------------------------------
+// mode 0: exponents float32[N][16] (game_dataset.py:15-21); mode 1: one-hot float32[N][16 ch][16 pos]
+// (game_dataset.py:46-48, mcts_nn.py:25-35).  One float4 per thread, consecutive threads write consecutive
+// 16-byte pieces (coalesced 512 B per warp).
+__global__ void encode_boards_kernel(const u64 *__restrict__ boards, int mode, float4 *__restrict__ out, long n) {
+    const long per = mode ? 64 : 4;  // float4 per board
+    const long total = n * per;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long b = i / per;
+        const int q = (int)(i - b * per);
+        const u64 x = __ldg(boards + b);
+        float4 v;
+        if (mode) {
+            const int c = q >> 2, p0 = (q & 3) * 4;  // channel, first of 4 positions
+            const u32 nib = (u32)(x >> (4 * p0)) & 0xFFFFu;
+            v.x = ((nib & 0xF) == (u32)c) ? 1.f : 0.f;
+            v.y = (((nib >> 4) & 0xF) == (u32)c) ? 1.f : 0.f;
+            v.z = (((nib >> 8) & 0xF) == (u32)c) ? 1.f : 0.f;
+            v.w = (((nib >> 12) & 0xF) == (u32)c) ? 1.f : 0.f;
+        } else {
+            const u32 nib = (u32)(x >> (16 * q)) & 0xFFFFu;
+            v.x = (float)(nib & 0xF);
+            v.y = (float)((nib >> 4) & 0xF);
+            v.z = (float)((nib >> 8) & 0xF);
+            v.w = (float)((nib >> 12) & 0xF);
+        }
+        out[i] = v;
+    }
+}
+
+// game_dataset.py:25-28: softmax(results / rowmax * soft) over the 4 root-move values of a record
+__global__ void soft_targets_kernel(const float4 *__restrict__ results, float soft, float4 *__restrict__ out, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float4 r = results[i];
+        const float mx = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
+        r.x = r.x / mx * soft, r.y = r.y / mx * soft, r.z = r.z / mx * soft, r.w = r.w / mx * soft;
+        const float m2 = fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w));
+        const float e0 = expf(r.x - m2), e1 = expf(r.y - m2), e2 = expf(r.z - m2), e3 = expf(r.w - m2);
+        const float inv = 1.f / (e0 + e1 + e2 + e3);
+        out[i] = make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
+    }
+}
+
 // root moves of G origins: legal flag, merge score and the moved board (mcts.py:21)
 __global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, long G, uint8_t *__restrict__ legal,
                                   u32 *__restrict__ rscore, u64 *__restrict__ rboard) {

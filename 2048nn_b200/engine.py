@@ -97,6 +97,24 @@ def policy_step(boards, prio, seed, k, gids=None, gid_base=0):
     return ob, gain, moved
 
 
+def encode_boards(boards, onehot=True):
+    """game_dataset.py:15-21 / 46-48: int64 boards -> float32 (N,16) exponents or (N,16,4,4) one-hot."""
+    d = _dev(boards)
+    n = boards.numel()
+    out = torch.empty((n, 16, 4, 4) if onehot else (n, 16), dtype=torch.float32, device=d)
+    L.check(L.load_library().b2048_encode_boards(L.ctx(d), L.ptr(boards), 1 if onehot else 0, L.ptr(out), n, L.stream_ptr(d)))
+    return out
+
+
+def soft_targets(results, soft=3.0):
+    """game_dataset.py:25-28: softmax(results / rowmax * soft), float32 (N,4) device tensor."""
+    d = _dev(results)
+    results = results.contiguous()
+    out = torch.empty_like(results)
+    L.check(L.load_library().b2048_soft_targets(L.ctx(d), L.ptr(results), float(soft), L.ptr(out), results.shape[0], L.stream_ptr(d)))
+    return out
+
+
 def rng_draws(n, seed, gid_base, first, count, device="cuda"):
     d = torch.device(device)
     out = torch.empty((n, count), dtype=torch.int64, device=d)

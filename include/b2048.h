@@ -100,6 +100,16 @@ int b2048_policy_step(b2048_ctx *ctx, const uint64_t *boards, const uint8_t *pri
                       const uint64_t *gids, uint64_t gid_base, const uint32_t *k, uint64_t *out_boards,
                       uint32_t *out_gain, uint8_t *out_moved, int64_t n, void *stream);
 
+/* Training-record encodings (game_dataset.py:6-48).
+ *   mode 0: tile exponents as float32[N*16] (position-major, game_dataset.py:15-21)
+ *   mode 1: one-hot planes float32[N*16*16] = (N,16,4,4), channel c is 1 where the cell's exponent is c
+ *           (game_dataset.py:46-48; the same tensor mcts_nn.py:25-35 feeds the network) */
+int b2048_encode_boards(b2048_ctx *ctx, const uint64_t *boards, int mode, float *out, int64_t n, void *stream);
+
+/* Soft targets of a self-play record: softmax(results / rowmax(results) * soft) over the 4 root-move values
+ * (game_dataset.py:25-28).  results, out: float32[N*4]. */
+int b2048_soft_targets(b2048_ctx *ctx, const float *results, float soft, float *out, int64_t n, void *stream);
+
 /* raw stream words for parity tests: out[g*count + j] = draw(first + j) of stream (seed, gid_base+g) */
 int b2048_rng_draws(b2048_ctx *ctx, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
                     uint64_t *out, int64_t n, void *stream);

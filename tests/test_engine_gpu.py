@@ -204,3 +204,46 @@ def test_both_playout_variants_are_bit_exact(eng, orc, eg):
                 assert (int(host_u64(f)[g]), int(s[g].item()), int(c[g].item())) == w
     finally:
         eng.set_playout_variant(1)
+
+
+def test_full_size_properties_16m_games(eng):
+    """BASELINE config[1] at its largest size (16M games): size-independent properties.
+    - every final board is dead (no legal move) and every game made progress;
+    - the closed-form score bookkeeping agrees with a recount from the final boards' tile sums:
+      sum of tiles on the final board == sum of tiles spawned (2 or 4 each, 2 tiles + one per move);
+    - results do not depend on how the batch is cut (gid_base offsets);
+    - the mean log10(score+1) matches the reference's published 3.3546 / 3.3508 (5000 games)."""
+    n = 1 << 24
+    f, s, c = eng.playout_fixed(n, 4711, 0)
+    _, _, legal = eng.board_ops(f, transpose=False, countzero=False)
+    assert int(legal.max().item()) == 0 and int(c.min().item()) >= 10
+    # tile-sum bound: all spawns are 2s or 4s, so 2*(moves+2) <= tilesum(final) <= 4*(moves+2)
+    expo = torch.stack([(f >> (4 * k)) & 0xF for k in range(16)], dim=1)
+    tsum = torch.where(expo > 0, torch.ones_like(expo) << expo, torch.zeros_like(expo)).sum(1)
+    spawned = c.to(torch.int64) + 2
+    assert bool(((tsum >= 2 * spawned) & (tsum <= 4 * spawned)).all())
+    # score = sum over tiles (t-1)*2^t - 4 * (#spawned 4s), and #4s = (tsum - 2*spawned)/2
+    pot = torch.where(expo > 0, (expo - 1) * (torch.ones_like(expo) << expo), torch.zeros_like(expo)).sum(1)
+    fours = (tsum - 2 * spawned) // 2
+    assert torch.equal(pot - 4 * fours, s.to(torch.int64))
+    # cutting the batch differently gives the same games
+    f2, s2, c2 = eng.playout_fixed(1 << 20, 4711, 5 << 20)
+    assert torch.equal(f2, f[5 << 20: 6 << 20]) and torch.equal(s2, s[5 << 20: 6 << 20]) and torch.equal(c2, c[5 << 20: 6 << 20])
+    m = torch.log10(s.to(torch.float64) + 1).mean().item()
+    assert abs(m - 3.3527) < 0.003, m
+
+
+def test_encode_kernel_streams_at_hbm_rate(eng):
+    # HBM-bound helper: 8 B in + 1,024 B out per board; must reach a sane fraction of the copy bandwidth
+    n = 1 << 21
+    b = eng.init_boards(n, 1, 0)
+    x = eng.encode_boards(b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x = eng.encode_boards(b)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = n * 1032 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    assert gbs > 2000, gbs
+    assert float(x.sum().item()) == n * 16.0
