@@ -222,6 +222,17 @@ __device__ __forceinline__ uint32_t act_off(int R, int c) { return (uint32_t)R *
 __device__ __forceinline__ int act_row(int x, int y, int b) { return (5 * x + 1 + y) * SLAB_ROWS + b; }
 
 
+// explicit shared-space accesses on 32-bit addresses: generic pointers derived from the aligned dynamic
+// smem base compile to 64-bit LD.E/ST.E with address arithmetic, which was measurably slower in the epilogue
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // {lo, hi} -> packed fp16x2 with ReLU folded into the conversion (cvt.rn.relu.f16x2.f32: one instruction)
 __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
     uint32_t d;
@@ -426,77 +437,58 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half) {
 //   ADD_RES  second conv of a block: add the block input kept in `res`
 //   KEEP_RES this output is a block input: remember it (packed fp16) in `res`
 //   LAST     last conv: do not write back; accumulate the 1x1 head conv on the fp32 values instead
-template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG, int W>
-__device__ __forceinline__ void epilogue_layer_w(uint8_t *row0, uint8_t *row1, int sw, const float *bias,
-                                                 const float *tail, uint32_t acc0, uint32_t (&res)[2][32],
-                                                 float (&head_acc)[2][4], float *dbg0) {
-    // W = columns drained per tcgen05.ld (8 or 16), both rows loaded together, one wait::ld per step.
-    // Register budget: res (64) dominates; measured on B200: W=8 joint loads beat per-row pipelining.
+// row0/row1, bias, tail are 32-bit shared-space addresses.
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
+__device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uint32_t sw16, uint32_t bias, uint32_t tail,
+                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
+                                               float *dbg0) {
+    // Both rows drained 8 columns at a time with one tcgen05.wait::ld per step.  Register budget: res (64)
+    // dominates.  Measured on B200: 16-column steps and per-row / double-buffered pipelining were not faster.
 #pragma unroll
-    for (int cw = 0; cw < 64 / W; cw++) {
-        float v[2][W];
-        if (W == 8) {
-            tmem_ld8(acc0 + (uint32_t)(cw * W), reinterpret_cast<uint32_t *>(v[0]));
-            tmem_ld8(acc0 + (uint32_t)(64 + cw * W), reinterpret_cast<uint32_t *>(v[1]));
-        } else {
-            tmem_ld16(acc0 + (uint32_t)(cw * W), reinterpret_cast<uint32_t *>(v[0]));
-            tmem_ld16(acc0 + (uint32_t)(64 + cw * W), reinterpret_cast<uint32_t *>(v[1]));
-        }
+    for (int c = 0; c < 8; c++) {  // 16-byte chunk = 8 channels
+        float v[2][8];
+        tmem_ld8(acc0 + (uint32_t)(c * 8), reinterpret_cast<uint32_t *>(v[0]));
+        tmem_ld8(acc0 + (uint32_t)(64 + c * 8), reinterpret_cast<uint32_t *>(v[1]));
+        const float4 b0 = lds_f4(bias + c * 32), b1 = lds_f4(bias + c * 32 + 16);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < W / 8; h++) {
-            const int c = cw * (W / 8) + h;  // 16-byte chunk = 8 channels
-            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int xi = 0; xi < 2; xi++) {
+            uint32_t pw[4];
 #pragma unroll
-            for (int xi = 0; xi < 2; xi++) {
-                uint4 pk;
-                uint32_t *pw = &pk.x;
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    float a0 = v[xi][h * 8 + 2 * jj] + bb[2 * jj];
-                    float a1 = v[xi][h * 8 + 2 * jj + 1] + bb[2 * jj + 1];
-                    if (ADD_RES) {
-                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
-                        a0 += f.x, a1 += f.y;
-                    }
-                    if (LAST || DBG) v[xi][h * 8 + 2 * jj] = fmaxf(a0, 0.f), v[xi][h * 8 + 2 * jj + 1] = fmaxf(a1, 0.f);
-                    if (!LAST) {
-                        pw[jj] = pack_relu_f16x2(a0, a1);
-                        if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
-                    }
+            for (int jj = 0; jj < 4; jj++) {
+                float a0 = v[xi][2 * jj] + bb[2 * jj];
+                float a1 = v[xi][2 * jj + 1] + bb[2 * jj + 1];
+                if (ADD_RES) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
+                    a0 += f.x, a1 += f.y;
                 }
-                if (!LAST) *reinterpret_cast<uint4 *>((xi ? row1 : row0) + ((c ^ sw) << 4)) = pk;
-                if (DBG && dbg0) {
-#pragma unroll
-                    for (int co = 0; co < 8; co++) dbg0[((c * 8 + co) * 16) + xi] = v[xi][h * 8 + co];
+                if (LAST || DBG) v[xi][2 * jj] = fmaxf(a0, 0.f), v[xi][2 * jj + 1] = fmaxf(a1, 0.f);
+                if (!LAST) {
+                    pw[jj] = pack_relu_f16x2(a0, a1);
+                    if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
                 }
-                if (LAST) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
+            }
+            if (!LAST) sts_u4((xi ? row1 : row0) + (((uint32_t)c << 4) ^ sw16), pw[0], pw[1], pw[2], pw[3]);
+            if (DBG && dbg0) {
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const float4 t0 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8);
-                        const float4 t1 = *reinterpret_cast<const float4 *>(tail + TAIL_W7 + c4 * 64 + c * 8 + 4);
-                        float sacc = head_acc[xi][c4];
-                        sacc = fmaf(v[xi][h * 8 + 0], t0.x, sacc), sacc = fmaf(v[xi][h * 8 + 1], t0.y, sacc);
-                        sacc = fmaf(v[xi][h * 8 + 2], t0.z, sacc), sacc = fmaf(v[xi][h * 8 + 3], t0.w, sacc);
-                        sacc = fmaf(v[xi][h * 8 + 4], t1.x, sacc), sacc = fmaf(v[xi][h * 8 + 5], t1.y, sacc);
-                        sacc = fmaf(v[xi][h * 8 + 6], t1.z, sacc), sacc = fmaf(v[xi][h * 8 + 7], t1.w, sacc);
-                        head_acc[xi][c4] = sacc;
-                    }
+                for (int co = 0; co < 8; co++) dbg0[((c * 8 + co) * 16) + xi] = v[xi][co];
+            }
+            if (LAST) {  // head 1x1 conv 64->4 on the fp32 values of this (board, position)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const float4 t0 = lds_f4(tail + (TAIL_W7 + c4 * 64 + c * 8) * 4);
+                    const float4 t1 = lds_f4(tail + (TAIL_W7 + c4 * 64 + c * 8 + 4) * 4);
+                    float sacc = head_acc[xi][c4];
+                    sacc = fmaf(v[xi][0], t0.x, sacc), sacc = fmaf(v[xi][1], t0.y, sacc);
+                    sacc = fmaf(v[xi][2], t0.z, sacc), sacc = fmaf(v[xi][3], t0.w, sacc);
+                    sacc = fmaf(v[xi][4], t1.x, sacc), sacc = fmaf(v[xi][5], t1.y, sacc);
+                    sacc = fmaf(v[xi][6], t1.z, sacc), sacc = fmaf(v[xi][7], t1.w, sacc);
+                    head_acc[xi][c4] = sacc;
                 }
             }
         }
     }
-}
-#ifndef B2048_EPI_W
-#define B2048_EPI_W 8
-#endif
-template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
-__device__ __forceinline__ void epilogue_layer(uint8_t *row0, uint8_t *row1, int sw, const float *bias, const float *tail,
-                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
-                                               float *dbg0) {
-    epilogue_layer_w<ADD_RES, KEEP_RES, LAST, DBG, B2048_EPI_W>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
 }
 
 // ---- worker groups -----------------------------------------------------------------------------------
@@ -594,14 +586,18 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
                 const long gb = *s_dbgbase + lane;
                 dbg0 = (dbg && dbg_layer == l && gb < dbg_n) ? dbg + gb * 1024 + (q * 4 + 2 * xg) : nullptr;
             }
-            if (l == 0)
-                epilogue_layer<false, true, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
-            else if (l & 1)
-                epilogue_layer<false, false, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
-            else if (l < N_LAYERS - 1)
-                epilogue_layer<true, true, false, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
-            else
-                epilogue_layer<true, false, true, DBG>(row0, row1, sw, bias, tail, acc0, res, head_acc, dbg0);
+            {
+                const uint32_t r0a = smem_u32(row0), r1a = smem_u32(row1), sw16 = (uint32_t)sw << 4;
+                const uint32_t ba = smem_u32(bias), ta = smem_u32(tail);
+                if (l == 0)
+                    epilogue_layer<false, true, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                else if (l & 1)
+                    epilogue_layer<false, false, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                else if (l < N_LAYERS - 1)
+                    epilogue_layer<true, true, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                else
+                    epilogue_layer<true, false, true, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+            }
             tc_fence_before();
             if (l < N_LAYERS - 1) {
                 fence_proxy_async();
