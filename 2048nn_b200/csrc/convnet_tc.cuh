@@ -607,27 +607,44 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             if (j == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 3);
             phase++;
         }
-        // ---- head: stage [board][c4*16 + pos] in the image's first data slab, FC by the owner warp --------
-        float *hb = reinterpret_cast<float *>(act + SLAB_ROWS * ROW_BYTES);
+        // ---- head: stage [board][c4*16 + pos] in the image's first data slab, then the FC over all 256
+        // threads of the group: thread -> (board = t/8, eighth of the 64 inputs), 8-lane shuffle reduction ----
+        {
+            const uint32_t hb = smem_u32(act + SLAB_ROWS * ROW_BYTES);
 #pragma unroll
-        for (int xi = 0; xi < 2; xi++) {
-            const int pos = q * 4 + xg * 2 + xi;
+            for (int xi = 0; xi < 2; xi++) {
+                const int pos = q * 4 + xg * 2 + xi;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) hb[lane * HEAD_STRIDE + c4 * 16 + pos] = fmaxf(head_acc[xi][c4], 0.f);
-        }
-        named_bar(bar_id, GROUP_WARPS * 32);
-        if (j == 0) {
-            float z[4];
+                for (int c4 = 0; c4 < 4; c4++)
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(hb + (uint32_t)(lane * HEAD_STRIDE + c4 * 16 + pos) * 4),
+                                 "f"(fmaxf(head_acc[xi][c4], 0.f))
+                                 : "memory");
+            }
+            named_bar(bar_id, GROUP_WARPS * 32);
+            const int t = j * 32 + lane, b = t >> 3, part = t & 7;
+            const uint32_t ta = smem_u32(tail);
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(hb + (uint32_t)(b * HEAD_STRIDE + part * 8 + i) * 4));
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    float w;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(ta + (uint32_t)(TAIL_FCW + o * 64 + part * 8 + i) * 4));
+                    z[o] = fmaf(x, w, z[o]);
+                }
+            }
 #pragma unroll
             for (int o = 0; o < 4; o++) {
-                float sacc = tail[TAIL_FCB + o];
-                const float *w = tail + TAIL_FCW + o * 64;
-#pragma unroll 8
-                for (int jj = 0; jj < 64; jj++) sacc = fmaf(hb[lane * HEAD_STRIDE + jj], w[jj], sacc);
-                z[o] = sacc;
+                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 1);
+                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 2);
+                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 4);
             }
-            *reinterpret_cast<float4 *>(s_logits + lane * 4) = make_float4(z[0], z[1], z[2], z[3]);
-            __syncwarp();
+            if (part == 0)
+                *reinterpret_cast<float4 *>(s_logits + b * 4) =
+                    make_float4(z[0] + tail[TAIL_FCB + 0], z[1] + tail[TAIL_FCB + 1], z[2] + tail[TAIL_FCB + 2], z[3] + tail[TAIL_FCB + 3]);
+            named_bar(bar_id, GROUP_WARPS * 32);
         }
         // the owner warp consumes s_logits in Work::step at the top of the loop; the other warps wait for
         // it at the group barrier there, so the image is not re-encoded before the head has been read.
