@@ -546,7 +546,6 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             if (lane == 0) mbar_arrive(bar_act);  // tells the MMA / producer warps that this set is done
             break;
         }
-        if (j == 0) Work::prefetch(wp, ws, sm + SM_CAND + set * 2048, lane);
         // ---- encode: one-hot rows (channels [0,16) and again [16,32) for the hi/lo weight split) --------
         {
             const unsigned long long brd = s_boards[lane];
@@ -569,6 +568,8 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_act);
+        // long-latency preparation of the NEXT step (candidate moves) overlaps the first layer's MMAs
+        if (j == 0) Work::prefetch(wp, ws, sm + SM_CAND + set * 2048, lane);
 
         float head_acc[2][4];
 #pragma unroll
