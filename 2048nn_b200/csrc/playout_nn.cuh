@@ -137,14 +137,17 @@ __device__ __forceinline__ void nn_move(const NNPlayParams &p, GameSlot &g, cons
     if (!moved) nn_finish(p, g);
 }
 
-// Candidate moves of a slot, computed while the network runs (PlayWork::prefetch) so that the move choice
-// after the forward is pure ALU work: the four moved boards, their merge scores and the group's current
-// minimum (slightly stale is fine: a larger bound only delays the early stop, the minimum is unaffected).
+// Candidate moves of a slot, computed while the network runs (PlayWork::prefetch): for each direction the
+// board AFTER the move and its spawn (the spawn draw depends only on the game's key and move count), the
+// merge score, a legality mask, and the group's current minimum (slightly stale is fine: a larger bound
+// only delays the early stop, the minimum itself is unaffected).  After the forward the move choice is a
+// handful of ALU instructions.
 struct SlotCand {
-    u64 board[4];
+    u64 next[4];
     u32 score[4];
     int gmin;
-    u32 pad[3];
+    u32 legal;  // bit d: direction d moves; bit 8+d: the move empties the board (randrange(0) in the reference)
+    u32 pad[2];
 };
 static_assert(sizeof(SlotCand) == 64, "SlotCand must be 64 bytes");
 
@@ -154,31 +157,29 @@ __device__ __forceinline__ void nn_move_cand(const NNPlayParams &p, GameSlot &g,
         nn_finish(p, g);
         return;
     }
-    // rank of each direction in descending logit order (stable: ties -> lower index first)
-    float zz[4] = {z[0], z[1], z[2], z[3]};
+    // highest logit among the legal directions (ties -> lower index, as the stable descending argsort)
     int best = -1;
     float bz = 0.f;
 #pragma unroll
     for (int d = 0; d < 4; d++) {
-        const bool legal = c.board[d] != g.board;
-        if (legal && (best < 0 || zz[d] > bz)) best = d, bz = zz[d];
+        const bool legal = (c.legal >> d) & 1u;
+        if (legal && (best < 0 || z[d] > bz)) best = d, bz = z[d];
     }
     if (best < 0) {
         nn_finish(p, g);
         return;
     }
-    u64 f = c.board[0];
-    u32 s = c.score[0];
-#pragma unroll
-    for (int d = 1; d < 4; d++)
-        if (best == d) f = c.board[d], s = c.score[d];
-    if (countzero(f) == 0) {
+    if ((c.legal >> (8 + best)) & 1u) {
         *p.err_flag = 1;
         nn_finish(p, g);
         return;
     }
-    u32 four;
-    g.board = spawn_tile(f, rng_draw(g.key, B2048_INIT_DRAWS + p.spawn0 + g.count), four);
+    u64 f = c.next[0];
+    u32 s = c.score[0];
+#pragma unroll
+    for (int d = 1; d < 4; d++)
+        if (best == d) f = c.next[d], s = c.score[d];
+    g.board = f;
     g.score += s;
     g.count++;
     moves_done++;
@@ -233,12 +234,25 @@ struct PlayWork {
     __device__ static void prefetch(const Params &p, State &st, uint8_t *scratch, int lane) {
         if (!st.g.live) return;
         SlotCand *c = reinterpret_cast<SlotCand *>(scratch) + lane;
+        const u64 draw = rng_draw(st.g.key, B2048_INIT_DRAWS + p.spawn0 + st.g.count);  // this move's spawn
+        u32 legal = 0;
 #pragma unroll
         for (int d = 0; d < 4; d++) {
             u32 s;
-            c->board[d] = move_exact(st.g.board, d, p.tb, s);
+            u64 f = move_exact(st.g.board, d, p.tb, s);
+            if (f != st.g.board) {
+                legal |= 1u << d;
+                if (countzero(f) == 0) {
+                    legal |= 1u << (8 + d);
+                } else {
+                    u32 four;
+                    f = spawn_tile(f, draw, four);
+                }
+            }
+            c->next[d] = f;
             c->score[d] = s;
         }
+        c->legal = legal;
         c->gmin = (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff;
     }
     __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
