@@ -181,7 +181,20 @@ def nn_policy_block(pkg, args, rank, world, barrier):
         _ = int(h_res[0, 0])  # host read of the step's result
     t1.record()
     barrier()
+    # config 5: forward-only sweep point (1M boards per GPU from policy-game positions), device timed
+    nb = 1 << 20
+    fb = eng.init_boards(nb, 99, rank * nb)
+    m.forward_boards(fb, precision="fp16")
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(3):
+        m.forward_boards(fb, precision="fp16")
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_boards_per_s = 3 * nb / (f0.elapsed_time(f1) * 1e-3)
     return {"ms": ms, "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "e2e_moves": float(e2e_moves.item()),
+            "fwd_boards_per_s": fwd_boards_per_s,
             "h2d": G * 8, "d2h": G * 4 * 8, "weights": weights,
             "workload": f"mcts_nn: {G} origins (fresh boards) x 4 root moves x {number} c64b3 policy lines per step, "
                         f"lines sharded over {world} GPU(s), [G,4] MIN allreduce per step"}
@@ -332,6 +345,9 @@ def main():
             "e2e": {"value": nn["e2e_moves"] / (nn["e2e_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": nn["h2d"], "d2h_bytes_per_step": nn["d2h"]},
             "gpu_launches": 2 * args.steps,
+            "forward_only": {"boards_per_s_per_gpu": nn["fwd_boards_per_s"], "boards": 1 << 20,
+                             "tflops_valid_taps": nn["fwd_boards_per_s"] * 5128704.0 / 1e12,
+                             "frac_of_sustained_peak": nn["fwd_boards_per_s"] * 5128704.0 / 1e12 / peaks["bf16_tflops_sustained"]},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": None,
                          "note": "5,128,704 valid-tap FLOP per policy evaluation x evals/s on one GPU vs the %s "
