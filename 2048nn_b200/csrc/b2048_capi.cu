@@ -390,7 +390,10 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         return 0;
     }
     if (precision == B2048_PREC_FP16_TC) {
-        int grid = grid_for(p.n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+        // few items: spread them over the SMs, one tile-set per CTA (lower per-step latency)
+        p.single_set = p.n <= (long)c->num_sms * tc::TILE_BOARDS;
+        int grid = p.single_set ? grid_for(p.n, tc::TILE_BOARDS, c->num_sms)
+                                : grid_for(p.n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
         tc::tc_persistent_kernel<PlayWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, (const uint8_t *)p.blob, nullptr,
                                                                                     -1, 0);
         CK(cudaGetLastError());

@@ -494,7 +494,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
 // ---- worker groups -----------------------------------------------------------------------------------
 // Work policy (owner warp = first warp of a group, all 32 lanes call it):
 //   struct Work { struct Params; struct State;
-//     static void init(State&);
+//     static void init(State&, const Params&, int set);
 //     // consume the previous forward's outputs (unless first), then provide the next 32 boards.
 //     // returns false when the set is finished.
 //     static bool step(const Params&, State&, bool first, const float *logits, unsigned long long *boards,
@@ -524,7 +524,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
     const int sw = lane & 7;  // SWIZZLE_128B phase of both rows (row index % 8 == lane % 8)
     const int bar_id = 1 + set;
     typename Work::State ws;
-    if (j == 0) Work::init(ws);
+    if (j == 0) Work::init(ws, wp, set);
     uint32_t phase = 0;
     bool first = true;
     uint32_t res[2][32];  // residual input of the current block, packed fp16
@@ -683,7 +683,7 @@ struct FwdWork {
     struct State {
         long base;
     };
-    __device__ static void init(State &st) { st.base = -1; }
+    __device__ static void init(State &st, const Params &, int) { st.base = -1; }
     __device__ static void prefetch(const Params &, State &, uint8_t *, int) {}
     __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
                                 int lane, long &dbg_base, uint8_t *) {

@@ -39,6 +39,7 @@ struct NNPlayParams {
     u32 *out_moves;
     unsigned long long *counter;
     unsigned long long *move_counter;  // total accepted moves (for throughput accounting), may be NULL
+    int single_set;                    // tensor-core kernel: use only tile-set 0 of every CTA (small batches)
     int *err_flag;
 };
 
@@ -225,11 +226,12 @@ struct PlayWork {
         u32 moves_done;
         bool queue_empty;
     };
-    __device__ static void init(State &st) {
+    __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
         st.g.board = 0;
         st.moves_done = 0;
-        st.queue_empty = false;
+        // latency mode (few work items): one tile-set per CTA so a step is not interleaved with a second set
+        st.queue_empty = (set > 0) && p.single_set;
     }
     __device__ static void prefetch(const Params &p, State &st, uint8_t *scratch, int lane) {
         if (!st.g.live) return;
