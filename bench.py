@@ -316,6 +316,12 @@ def main():
     issue_peak = sm_count * 4 * 32 * peaks["sm_max_mhz"] * 1e6  # thread-instr/s at max SM clock
     achieved = per_gpu_moves_per_s * INSTR_PER_MOVE
     hbm_bytes = 24.0 * n * args.steps  # 8 B start + 16 B results per game
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same size only)
+    tpath = os.path.join(ROOT, "profiles", "r01_k2_traffic_16m.json")
+    if os.path.exists(tpath):
+        tinfo = json.load(open(tpath))
+        if tinfo.get("games") == n:
+            traffic = tinfo["traffic_bytes_per_launch"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,7 +334,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": args.steps,
         "roofline": {"bound": "sm_issue", "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
-                     "frac": achieved / issue_peak, "traffic": None,
+                     "frac": achieved / issue_peak, "traffic": traffic,
                      "note": "algorithmic 250 thread-instr/move x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); "
                              "the kernel is integer-issue bound, HBM sees only %.1f GB/s of %.0f"
                              % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
