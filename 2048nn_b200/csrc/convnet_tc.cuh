@@ -10,8 +10,8 @@
 //     (1+dy)*32 -- the zero rows supply the y padding, out-of-range columns are skipped, so
 //     no shifted copies and no masked loads.
 //   * One A operand feeds up to three output columns: for input slab s and a given dy,
-//     D[x=s-1 | x=s | x=s+1] += A(s,dy) * [W(dy,+1); W(dy,0); W(dy,-1)]^T is ONE
-//     tcgen05.mma with N = 192 (128 at the borders) into adjacent TMEM column blocks.
+//     D[x=s-1 | x=s | x=s+1] += A(s,dy) * [W(dy,+1); W(dy,0); W(dy,-1)]^T lands in adjacent TMEM
+//     column blocks (issued as N = 128 / 64 pieces by two warps that own disjoint block halves).
 //   * Accumulators: TMEM, per tile-set 4 column blocks x 64 fp32 columns (one per board column x);
 //     two tile-sets = all 512 columns.
 //   * Weights (fp16, BatchNorm folded) stream from L2 as 24 KB pre-swizzled chunks
@@ -29,8 +29,8 @@
 //
 // Warp roles (640 threads): warps 0..7 = workers of set A, warps 8..15 = workers of set B (encode,
 // epilogues, head; the first warp of each group also owns the set's 32 boards / game slots),
-// warp 16 = weight producer, warp 17 = MMA issuer (+TMEM owner), warps 18..19 idle.  setmaxnreg
-// moves registers from the control warpgroup to the four worker warpgroups.
+// warp 16 = weight producer, warps 17, 18 = MMA issuers (accumulator halves; 17 owns TMEM), warp 19 idle.
+// setmaxnreg moves registers from the control warpgroup to the four worker warpgroups.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -106,20 +106,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// non-blocking probe: true when the phase with this parity has completed
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -137,20 +123,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate), issued by one thread
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Same, executed by ALL lanes of the (converged) MMA warp with warp-uniform operands; one elected lane
-// issues.  Keeping the descriptor arithmetic warp-uniform lets ptxas hold the operands in uniform registers
+// D[tmem] += A[smem] * B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate).  Executed by ALL lanes of the
+// (converged) MMA warp with warp-uniform operands; one elected lane issues.  Keeping the descriptor arithmetic warp-uniform lets ptxas hold the operands in uniform registers
 // instead of a per-MMA R2UR/ELECT waterfall (measured: the issue path, not the tensor pipe, set the pace).
 __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -173,31 +147,6 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
         "}" ::"r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 columns of fp32 -> 32 registers per thread (thread t <-> TMEM lane base+t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -206,19 +155,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14), LBO>>4 [16,30) = 0, SBO>>4 [32,46) = 1024 B (8 rows x 128 B), version 1 [46,48),
-// layout SWIZZLE_128B = 2 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
-}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) = 0, SBO>>4 [32,46) = 1024 B (8 rows x 128 B), version 1 [46,48), layout SWIZZLE_128B = 2
+// [61,64).  The constant upper part is `desc_hi` in mma_loop; the low word is (shared address >> 4).
 // kind::f16 instruction descriptor: D fp32 (bit 4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// byte offset of 16-byte chunk c of activation row R (SWIZZLE_128B: chunk ^= row % 8)
-__device__ __forceinline__ uint32_t act_off(int R, int c) { return (uint32_t)R * ROW_BYTES + (uint32_t)((c ^ (R & 7)) << 4); }
+// activation row R of (column x, board row y, board b); its 16-byte chunk c lives at chunk c ^ (R % 8) (SWIZZLE_128B)
 __device__ __forceinline__ int act_row(int x, int y, int b) { return (5 * x + 1 + y) * SLAB_ROWS + b; }
 
 

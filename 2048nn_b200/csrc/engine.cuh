@@ -134,7 +134,7 @@ __device__ __forceinline__ u64 spawn_tile(u64 board, u64 draw, u32 &is_four) {
 }
 
 // generate_init_tiles (board.py:68-82) on the game's word stream (words 0..15 reserved).
-__device__ __forceinline__ u64 init_board_slow(u64 key);
+__device__ u64 init_board_slow(u64 key);
 __device__ __forceinline__ u64 init_board(u64 key) {
     // common case (15/16): pos1 != pos2 on the first try -> words 0..3 = two draws
     const u64 d0 = rng_draw(key, 0), d1 = rng_draw(key, 1);
