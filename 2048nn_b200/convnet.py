@@ -67,8 +67,17 @@ def _swizzle_rows(rows_u16):
     return out.reshape(R, 64)
 
 
-def pack_tc(folded):
-    """fp16 tensor-core blob: 21 chunks (layer l, ky) of 192 rows [kx=2 | kx=1 | kx=0] x 64 co, each row
+def _to16(x, dtype):
+    """float array -> (uint16 bit patterns, float32 values after rounding) in fp16 or bf16"""
+    if dtype == "fp16":
+        h = np.asarray(x, np.float32).astype(np.float16)
+        return h.view(np.uint16), h.astype(np.float32)
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16)
+    return t.view(torch.int16).numpy().view(np.uint16), t.to(torch.float32).numpy()
+
+
+def pack_tc(folded, dtype="fp16"):
+    """16-bit tensor-core blob (dtype "fp16" or "bf16"): 21 chunks (layer l, ky) of 192 rows [kx=2 | kx=1 | kx=0] x 64 co, each row
     64 ci fp16 (K-major, pre-swizzled); L0 rows are [W_hi(16 ci) | W_lo(16 ci) | 0]; then the fp32 tail
     bias[7][64], w7[4][64], b7[4], fcw[4][64], fcb[4]."""
     chunks = []
@@ -79,16 +88,16 @@ def pack_tc(folded):
             for blk, kx in enumerate((2, 1, 0)):  # dx = +1, 0, -1  ->  output column x = s-1, s, s+1
                 wk = w[:, :, ky, kx]  # (co, ci)
                 if l == 0:
-                    hi = wk.astype(np.float16)
-                    lo = (wk - hi.astype(np.float64)).astype(np.float16)
-                    rows[blk * 64:(blk + 1) * 64, 0:16] = hi.astype(np.float32)
-                    rows[blk * 64:(blk + 1) * 64, 16:32] = lo.astype(np.float32)
+                    _, hi = _to16(wk, dtype)
+                    _, lo = _to16(wk - hi.astype(np.float64), dtype)
+                    rows[blk * 64:(blk + 1) * 64, 0:16] = hi
+                    rows[blk * 64:(blk + 1) * 64, 16:32] = lo
                 else:
                     rows[blk * 64:(blk + 1) * 64, :] = wk.astype(np.float32)
-            h = rows.astype(np.float16)
-            if not np.isfinite(h.astype(np.float32)).all():
-                raise ValueError("folded weights overflow fp16")
-            chunks.append(_swizzle_rows(h.view(np.uint16)).reshape(-1))
+            bits, vals = _to16(rows, dtype)
+            if not np.isfinite(vals).all():
+                raise ValueError("folded weights overflow " + dtype)
+            chunks.append(_swizzle_rows(bits).reshape(-1))
     wbytes = np.concatenate(chunks).view(np.uint8)
     tail = np.concatenate([np.stack(folded["conv_b"]).reshape(-1), folded["head_w"].reshape(-1), folded["head_b"],
                            folded["fc_w"].reshape(-1), folded["fc_b"]]).astype(np.float32)

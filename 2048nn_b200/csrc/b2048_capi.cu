@@ -97,6 +97,10 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(playout_nn_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_FP32_SMEM_BYTES));
     *out = c;
     return 0;
@@ -317,7 +321,7 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t b2048_convnet_blob_bytes(int precision) {
     if (precision == B2048_PREC_FP32) return (int64_t)CN_FP32_FLOATS * 4;
-    if (precision == B2048_PREC_FP16_TC) return (int64_t)tc::BLOB_BYTES;
+    if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC) return (int64_t)tc::BLOB_BYTES;
     return -1;
 }
 
@@ -333,7 +337,7 @@ static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st) {
 }
 
 static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logp, float *out_logits,
-                             float *dbg, int dbg_layer, int64_t n, cudaStream_t st) {
+                             float *dbg, int dbg_layer, int64_t n, cudaStream_t st, bool bf16 = false) {
     tc::FwdWork::Params p;
     p.boards = (const unsigned long long *)boards;
     p.out_logp = out_logp;
@@ -346,6 +350,9 @@ static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boa
     if (dbg)
         tc::tc_persistent_kernel<tc::FwdWork, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, dbg, dbg_layer, (long)n);
+    else if (bf16)
+        tc::tc_persistent_kernel<tc::FwdWork, false, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            p, (const uint8_t *)blob, nullptr, -1, (long)n);
     else
         tc::tc_persistent_kernel<tc::FwdWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, nullptr, -1, (long)n);
@@ -365,7 +372,8 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
         CK(cudaGetLastError());
         return 0;
     }
-    if (precision == B2048_PREC_FP16_TC) return launch_tc_forward(c, blob, boards, out_logp, nullptr, nullptr, -1, n, st);
+    if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC)
+        return launch_tc_forward(c, blob, boards, out_logp, nullptr, nullptr, -1, n, st, precision == B2048_PREC_BF16_TC);
     return fail_msg("b2048_convnet_forward: unknown precision");
 }
 
@@ -389,13 +397,17 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         CK(cudaGetLastError());
         return 0;
     }
-    if (precision == B2048_PREC_FP16_TC) {
+    if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC) {
         // few items: spread them over the SMs, one tile-set per CTA (lower per-step latency)
         p.single_set = p.n <= (long)c->num_sms * tc::TILE_BOARDS;
         int grid = p.single_set ? grid_for(p.n, tc::TILE_BOARDS, c->num_sms)
                                 : grid_for(p.n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
-        tc::tc_persistent_kernel<PlayWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, (const uint8_t *)p.blob, nullptr,
-                                                                                    -1, 0);
+        if (precision == B2048_PREC_BF16_TC)
+            tc::tc_persistent_kernel<PlayWork, false, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        else
+            tc::tc_persistent_kernel<PlayWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
         CK(cudaGetLastError());
         return 0;
     }

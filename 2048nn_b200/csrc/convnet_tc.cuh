@@ -159,8 +159,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // LBO>>4 [16,30) = 0, SBO>>4 [32,46) = 1024 B (8 rows x 128 B), version 1 [46,48), layout SWIZZLE_128B = 2
 // [61,64).  The constant upper part is `desc_hi` in mma_loop; the low word is (shared address >> 4).
 // kind::f16 instruction descriptor: D fp32 (bit 4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// A/B format at [7,10) / [10,13): 0 = fp16, 1 = bf16
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool bf16 = false) {
+    return (1u << 4) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // activation row R of (column x, board row y, board b); its 16-byte chunk c lives at chunk c ^ (R % 8) (SWIZZLE_128B)
@@ -179,6 +180,20 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // {lo, hi} -> packed fp16x2 with ReLU folded into the conversion (cvt.rn.relu.f16x2.f32: one instruction)
+// 16-bit operand format helpers: BF16 = false -> fp16 (default, meets the parity bar), true -> bf16 (the
+// north-star's nominal format; measurably fails the bar on the shipped weights, kept for comparison)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack_relu_x2(float lo, float hi) {
+    uint32_t d;
+    if (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool BF16>
+__device__ __forceinline__ float2 unpack_x2(uint32_t u) {
+    if (BF16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
 __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
@@ -301,7 +316,7 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) 
 // Same tensor work as one N=128/192/192/128 sweep, each half's first MMA (dy=-1, k=0) is its own first
 // writer (overwrite), and no ordering between the two issuers is needed.
 __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi,
-                                           int nk, int half) {
+                                           int nk, int half, bool bf16) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         // (slab, first B row, N, first D column) of this half's i-th MMA group; chunk rows are
@@ -310,7 +325,7 @@ __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32
         const int brow = half == 0 ? (i == 0 ? 64 : 0) : (i == 0 ? 0 : (i == 1 ? 64 : 128));
         const int N = (i == 2) ? 64 : 128;
         const int dcol = half == 0 ? (i == 2 ? 64 : 0) : 128;
-        const uint32_t idesc = make_idesc(128, N);
+        const uint32_t idesc = make_idesc(128, N, bf16);
         // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
         const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
         const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
@@ -322,7 +337,7 @@ __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32
     }
 }
 
-__device__ __forceinline__ void mma_loop(uint8_t *sm, int half) {
+__device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
     const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
@@ -361,7 +376,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half) {
                     tc_fence_after();
                     // whole warp, uniform operands, one elected lane issues; tmem_base is 0 (all 512 columns owned)
                     issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                               (uint32_t)(set * 256), desc_hi, dyi, nk, half);
+                               (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16);
                     if (dyi == 2) umma_commit_elect(bars.acc0 + 8 * set);  // this half of the set's accumulators
                     if (dyi == 2 && half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
                     if (dyi == 2) phase[set]++;
@@ -383,7 +398,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half) {
 //   KEEP_RES this output is a block input: remember it (packed fp16) in `res`
 //   LAST     last conv: do not write back; accumulate the 1x1 head conv on the fp32 values instead
 // row0/row1, bias, tail are 32-bit shared-space addresses.
-template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG>
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG, bool BF16>
 __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uint32_t sw16, uint32_t bias, uint32_t tail,
                                                uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
                                                float *dbg0) {
@@ -405,12 +420,12 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
                 float a0 = v[xi][2 * jj] + bb[2 * jj];
                 float a1 = v[xi][2 * jj + 1] + bb[2 * jj + 1];
                 if (ADD_RES) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&res[xi][c * 4 + jj]));
+                    const float2 f = unpack_x2<BF16>(res[xi][c * 4 + jj]);
                     a0 += f.x, a1 += f.y;
                 }
                 if (LAST || DBG) v[xi][2 * jj] = fmaxf(a0, 0.f), v[xi][2 * jj + 1] = fmaxf(a1, 0.f);
                 if (!LAST) {
-                    pw[jj] = pack_relu_f16x2(a0, a1);
+                    pw[jj] = pack_relu_x2<BF16>(a0, a1);
                     if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
                 }
             }
@@ -447,7 +462,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
 //     // called right after the boards are published: start long-latency work for the NEXT step() so that it
 //     // overlaps the forward (scratch = 64 B of shared memory per slot)
 //     static void prefetch(const Params&, State&, uint8_t *scratch, int lane); };
-template <class Work, bool DBG>
+template <class Work, bool DBG, bool BF16>
 __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, const typename Work::Params &wp, int set,
                                             int j, float *dbg, int dbg_layer, long dbg_n) {
     const uint32_t sm_base = smem_u32(sm);
@@ -498,7 +513,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             for (int xi = 0; xi < 2; xi++) {
                 const int t = (int)((brd >> (4 * (q * 4 + 2 * xg + xi))) & 0xF);
                 uint8_t *row = xi ? row1 : row0;
-                const uint32_t one = 0x3C00u << ((t & 1) * 16);  // fp16 1.0 in the right half-word
+                const uint32_t one = (BF16 ? 0x3F80u : 0x3C00u) << ((t & 1) * 16);  // 1.0 in the right half-word
                 const int wsel = (t & 7) >> 1;
                 const uint4 hot = make_uint4(wsel == 0 ? one : 0u, wsel == 1 ? one : 0u, wsel == 2 ? one : 0u,
                                              wsel == 3 ? one : 0u);
@@ -536,13 +551,13 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
                 const uint32_t r0a = smem_u32(row0), r1a = smem_u32(row1), sw16 = (uint32_t)sw << 4;
                 const uint32_t ba = smem_u32(bias), ta = smem_u32(tail);
                 if (l == 0)
-                    epilogue_layer<false, true, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<false, true, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (l & 1)
-                    epilogue_layer<false, false, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<false, false, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (l < N_LAYERS - 1)
-                    epilogue_layer<true, true, false, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<true, true, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else
-                    epilogue_layer<true, false, true, DBG>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<true, false, true, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
             }
             tc_fence_before();
             if (l < N_LAYERS - 1) {
@@ -598,7 +613,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
 }
 
 // Generic persistent kernel: producer + MMA issuer + NSETS worker groups.
-template <class Work, bool DBG>
+template <class Work, bool DBG, bool BF16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float *dbg, int dbg_layer, long dbg_n) {
     extern __shared__ uint8_t smem_raw[];
@@ -607,11 +622,11 @@ tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float 
     const int warp = threadIdx.x >> 5;
     if (warp < WORKER_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
-        worker_loop<Work, DBG>(sm, tmem_base, wp, warp / GROUP_WARPS, warp % GROUP_WARPS, dbg, dbg_layer, dbg_n);
+        worker_loop<Work, DBG, BF16>(sm, tmem_base, wp, warp / GROUP_WARPS, warp % GROUP_WARPS, dbg, dbg_layer, dbg_n);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
         if (warp == PRODUCER_WARP) producer_loop(sm, blob);
-        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop(sm, warp - MMA_WARP);
+        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop(sm, warp - MMA_WARP, BF16);
     }
     tc_teardown(tmem_base);
 }

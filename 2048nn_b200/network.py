@@ -7,7 +7,9 @@ and returns `(N,4)` log-probabilities computed by the CUDA kernels (b2048_convne
 `forward_boards` takes packed uint64 boards directly (8 B instead of 1,024 B per board).
 
 precision: "fp32" = exact mode (CUDA-core FMA, |dlogp| ~1e-5 vs PyTorch);
-           "fp16" = tcgen05 tensor-core mode (fp16 operands, fp32 accumulation).
+           "fp16" = tcgen05 tensor-core mode (fp16 operands, fp32 accumulation);
+           "bf16" = the same kernels with bf16 operands (fails the 99.9 % argmax bar on the shipped
+                    weights; kept so the choice of fp16 is a measurement, not an assumption).
 Training (autograd through forward) is outside this path and raises.
 """
 import torch
@@ -16,7 +18,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import convnet as _cn
 
-PRECISIONS = {"fp32": 0, "fp16": 1}
+PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2}
 
 
 class ConvNet(nn.Module):
@@ -55,7 +57,7 @@ class ConvNet(nn.Module):
             if precision == "fp32":
                 b = _cn.pack_fp32(folded)
             else:
-                b = _cn.pack_tc(folded)
+                b = _cn.pack_tc(folded, precision)
             dev = next(self.parameters()).device
             dev = dev if dev.type == "cuda" else torch.device("cuda")
             self._blob, self._blob_key = b.to(dev), key
@@ -97,7 +99,7 @@ def blob_for(model, precision=None):
     key = (precision, tuple((p.data_ptr(), p._version) for p in model.state_dict().values()))
     if cache.get("key") != key:
         folded = _cn.fold_state_dict(model.state_dict())
-        b = _cn.pack_fp32(folded) if precision == "fp32" else _cn.pack_tc(folded)
+        b = _cn.pack_fp32(folded) if precision == "fp32" else _cn.pack_tc(folded, precision)
         L.require_cuda()
         cache["key"], cache["blob"] = key, b.cuda()
     return cache["blob"], precision

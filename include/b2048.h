@@ -152,6 +152,7 @@ int b2048_mcts_fixed(b2048_ctx *ctx, const uint64_t *origins, int64_t G, int num
  * ------------------------------------------------------------------------------------------ */
 #define B2048_PREC_FP32 0
 #define B2048_PREC_FP16_TC 1
+#define B2048_PREC_BF16_TC 2 /* same kernels with bf16 operands: fails the parity bar on the shipped weights, for comparison */
 
 /* size in bytes of the weight blob for a precision (-1: unsupported) */
 int64_t b2048_convnet_blob_bytes(int precision);

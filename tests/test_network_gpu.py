@@ -159,3 +159,18 @@ def test_shipped_net_quality_pin(pkg, models):
     for k in range(16):
         mx = np.maximum(mx, ((f >> np.uint64(4 * k)) & np.uint64(15)).astype(np.int64))
     assert abs((mx >= 11).mean() - 0.24) < 0.04
+
+
+def test_bf16_mode_measured_against_the_bar(models, ng):
+    # The north star names bf16 operands; on the shipped weights bf16 misses the 99.9 % argmax bar (SURVEY.md
+    # Appendix C predicted 99.6 %), which is why fp16 is the default.  Same kernels, same layout.
+    b = dev_boards(ng["lg_boards"])
+    ref = ng["lg_shipped"]
+    lp16 = models["shipped"].forward_boards(b, precision="fp16").cpu().numpy()
+    lpb = models["shipped"].forward_boards(b, precision="bf16").cpu().numpy()
+    a16 = (lp16.argmax(1) == ref.argmax(1)).mean()
+    ab = (lpb.argmax(1) == ref.argmax(1)).mean()
+    assert np.abs(lpb - ref).max() < 0.5 and ab > 0.99      # bf16 works ...
+    assert ab < a16 and np.abs(lpb - ref).max() > np.abs(lp16 - ref).max()  # ... but is strictly worse than fp16
+    lpr = models["random"].forward_boards(b, precision="bf16").cpu().numpy()
+    assert np.abs(lpr - ng["lg_random"]).max() < 5e-3
