@@ -45,6 +45,7 @@ _SIGS = {
     "b2048_convnet_forward": (C.c_int, [P, C.c_int, P, P, P, i64, P]),
     "b2048_convnet_tc_debug": (C.c_int, [P, P, P, P, P, C.c_int, i64, P]),
     "b2048_playout_nn": (C.c_int, [P, C.c_int, P, P, u64, u64, u32, C.c_int, P, P, P, P, P, i64, P]),
+    "b2048_playout_nn_population": (C.c_int, [P, C.c_int, P, i64, C.c_int, P, u64, u64, u64, C.c_int, P, P, P, P, P, i64, P]),
     "b2048_mcts_nn": (C.c_int, [P, C.c_int, P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P]),
     "b2048_mcts_fixed": (C.c_int, [P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P, P, P]),
 }

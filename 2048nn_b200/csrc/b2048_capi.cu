@@ -388,20 +388,33 @@ extern "C" int b2048_convnet_tc_debug(b2048_ctx *c, const void *blob, const uint
 static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t st) {
     p.tb = tables_of(c);
     p.err_flag = c->err_flag;
-    unsigned slot = (c->next_counter++) % N_COUNTERS;
+    const int models = p.n_models > 1 ? p.n_models : 1;
+    if (models > N_COUNTERS || models > c->num_sms) return fail_msg("b2048 NN playout: too many models in one launch");
+    // `models` consecutive work cursors out of the rotating pool
+    unsigned slot = c->next_counter % N_COUNTERS;
+    if (slot + (unsigned)models > N_COUNTERS) slot = 0;
+    c->next_counter = slot + (unsigned)models;
     p.counter = c->counters + slot;
-    CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * models, st));
+    const long total = p.n * models;
     if (precision == B2048_PREC_FP32) {
-        int grid = grid_for(p.n, CN_BOARDS_PER_CTA, c->num_sms * 2);
+        int grid = models > 1 ? c->num_sms * 2 : grid_for(p.n, CN_BOARDS_PER_CTA, c->num_sms * 2);
         playout_nn_fp32_kernel<<<grid, 512, CN_FP32_SMEM_BYTES, st>>>(p);
         CK(cudaGetLastError());
         return 0;
     }
     if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC) {
-        // few items: spread them over the SMs, one tile-set per CTA (lower per-step latency)
-        p.single_set = p.n <= (long)c->num_sms * tc::TILE_BOARDS;
-        int grid = p.single_set ? grid_for(p.n, tc::TILE_BOARDS, c->num_sms)
-                                : grid_for(p.n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+        int grid;
+        if (models > 1) {
+            // every CTA is bound to one model; a model's games spread over its num_sms / models CTAs
+            grid = c->num_sms;
+            p.single_set = p.n <= (long)(grid / models) * tc::TILE_BOARDS;
+        } else {
+            // few items: spread them over the SMs, one tile-set per CTA (lower per-step latency)
+            p.single_set = total <= (long)c->num_sms * tc::TILE_BOARDS;
+            grid = p.single_set ? grid_for(total, tc::TILE_BOARDS, c->num_sms)
+                                : grid_for(total, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+        }
         if (precision == B2048_PREC_BF16_TC)
             tc::tc_persistent_kernel<PlayWork, false, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
@@ -435,6 +448,42 @@ extern "C" int b2048_playout_nn(b2048_ctx *c, int precision, const void *blob, c
     p.out_moves = out_moves;
     p.move_counter = (unsigned long long *)move_counter;
     return launch_nn(c, precision, p, (cudaStream_t)stream);
+}
+
+extern "C" int b2048_playout_nn_population(b2048_ctx *c, int precision, const void *blobs, int64_t blob_stride,
+                                           int n_models, const uint64_t *start, uint64_t seed, uint64_t gid_base,
+                                           uint64_t gid_model_stride, int group_size, int32_t *group_min,
+                                           uint64_t *out_final, uint32_t *out_score, uint32_t *out_moves,
+                                           uint64_t *move_counter, int64_t n_per_model, void *stream) {
+    if (n_per_model <= 0 || n_models <= 0) return 0;
+    if (!blobs) return fail_msg("b2048_playout_nn_population: blobs is NULL");
+    if (blob_stride <= 0 || (blob_stride & 15)) return fail_msg("b2048_playout_nn_population: blob_stride must be a positive multiple of 16");
+    if (group_min && group_size > 0 && n_per_model % group_size)
+        return fail_msg("b2048_playout_nn_population: n_per_model must be a multiple of group_size");
+    const int per_launch = c->num_sms < N_COUNTERS ? c->num_sms : N_COUNTERS;
+    for (int m0 = 0; m0 < n_models; m0 += per_launch) {
+        const int mc = (n_models - m0) < per_launch ? (n_models - m0) : per_launch;
+        NNPlayParams p;
+        memset(&p, 0, sizeof p);
+        p.blob = (const uint8_t *)blobs + (size_t)m0 * (size_t)blob_stride;
+        p.n = (long)n_per_model;
+        p.n_models = mc;
+        p.blob_stride = (long)blob_stride;
+        p.gid_model_stride = gid_model_stride;
+        p.start = (const u64 *)start;
+        p.seed = seed;
+        p.gid_base = gid_base + (uint64_t)m0 * gid_model_stride;
+        p.group_size = group_size;
+        const size_t o = (size_t)m0 * (size_t)n_per_model;
+        p.group_min = (group_min && group_size > 0) ? group_min + o / group_size : nullptr;
+        p.out_final = out_final ? (u64 *)out_final + o : nullptr;
+        p.out_score = out_score ? out_score + o : nullptr;
+        p.out_moves = out_moves ? out_moves + o : nullptr;
+        p.move_counter = (unsigned long long *)move_counter;
+        if (mc == 1) p.n_models = 0;
+        if (int rc = launch_nn(c, precision, p, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
 }
 
 extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, const uint64_t *origins, int64_t G,

@@ -454,6 +454,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
 // ---- worker groups -----------------------------------------------------------------------------------
 // Work policy (owner warp = first warp of a group, all 32 lanes call it):
 //   struct Work { struct Params; struct State;
+//     static size_t blob_offset(const Params&);   // byte offset of this CTA's weight image (multi-model launches)
 //     static void init(State&, const Params&, int set);
 //     // consume the previous forward's outputs (unless first), then provide the next 32 boards.
 //     // returns false when the set is finished.
@@ -617,6 +618,7 @@ template <class Work, bool DBG, bool BF16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float *dbg, int dbg_layer, long dbg_n) {
     extern __shared__ uint8_t smem_raw[];
+    blob += Work::blob_offset(wp);
     uint32_t tmem_base;
     uint8_t *sm = tc_setup(smem_raw, blob, tmem_base);
     const int warp = threadIdx.x >> 5;
@@ -643,6 +645,7 @@ struct FwdWork {
     struct State {
         long base;
     };
+    __device__ static size_t blob_offset(const Params &) { return 0; }
     __device__ static void init(State &st, const Params &, int) { st.base = -1; }
     __device__ static void prefetch(const Params &, State &, uint8_t *, int) {}
     __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,

@@ -40,6 +40,12 @@ struct NNPlayParams {
     unsigned long long *counter;
     unsigned long long *move_counter;  // total accepted moves (for throughput accounting), may be NULL
     int single_set;                    // tensor-core kernel: use only tile-set 0 of every CTA (small batches)
+    // population mode (evolve.py:30-36: the same evaluation for every network of a population): CTA c plays for
+    // model c % n_models with that model's weights at blob + model*blob_stride and work cursor counter[model];
+    // `n` is then the number of games PER MODEL and outputs are indexed model*n + game
+    int n_models;          // <= 1: single model
+    long blob_stride;      // bytes between consecutive models' weight images
+    u64 gid_model_stride;  // game id offset per model (0: every model sees the same spawn streams)
     int *err_flag;
 };
 
@@ -53,8 +59,9 @@ struct GameSlot {
 
 // fetch + initialise one work item into `g`; returns false when the queue is empty.
 __device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
+    const int model = p.n_models > 1 ? (int)(blockIdx.x % (unsigned)p.n_models) : 0;
     for (;;) {
-        long item = (long)atomicAdd(p.counter, 1ULL);
+        long item = (long)atomicAdd(p.counter + model, 1ULL);
         if (item >= p.n) return false;
         g.score = 0;
         g.count = 0;
@@ -79,11 +86,11 @@ __device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
             g.board = spawn_tile(rb, rng_draw(g.key, B2048_INIT_DRAWS), four);  // mcts_nn.py:22
             if (p.group_min) g.group = (int)r;
         } else {
-            g.slot = item;
-            g.key = rng_key(p.seed, p.gid_base + (u64)item);
+            g.slot = (long)model * p.n + item;
+            g.key = rng_key(p.seed, p.gid_base + (u64)model * p.gid_model_stride + (u64)item);
             u64 s0 = p.start ? p.start[item] : 0ULL;
             g.board = s0 ? s0 : init_board(g.key);
-            if (p.group_min && p.group_size > 0) g.group = (int)(item / p.group_size);
+            if (p.group_min && p.group_size > 0) g.group = (int)(g.slot / p.group_size);
         }
         g.live = 1;
         return true;
@@ -198,6 +205,8 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
     u32 moves_done = 0;
     bool queue_empty = false;
     const int t = threadIdx.x;
+    const float *blob = reinterpret_cast<const float *>(
+        reinterpret_cast<const uint8_t *>(p.blob) + (p.n_models > 1 ? (size_t)(blockIdx.x % (unsigned)p.n_models) * p.blob_stride : 0));
     for (;;) {
         if (t == 0) s_live = 0;
         __syncthreads();
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
         }
         __syncthreads();
         if (!s_live) break;
-        convnet_fp32_cta(reinterpret_cast<const float *>(p.blob), s_boards, CN_BOARDS_PER_CTA, act0, act1, s_head, s_logits);
+        convnet_fp32_cta(blob, s_boards, CN_BOARDS_PER_CTA, act0, act1, s_head, s_logits);
         if (t < CN_BOARDS_PER_CTA && g.live) nn_move(p, g, s_logits + 4 * t, moves_done);
         __syncthreads();
     }
@@ -226,6 +235,9 @@ struct PlayWork {
         u32 moves_done;
         bool queue_empty;
     };
+    __device__ static size_t blob_offset(const Params &p) {
+        return p.n_models > 1 ? (size_t)(blockIdx.x % (unsigned)p.n_models) * (size_t)p.blob_stride : 0;
+    }
     __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
         st.g.board = 0;

@@ -177,6 +177,32 @@ def playout_nn(blob, precision, n, seed, gid_base=0, start=None, spawn0=0, group
     return r
 
 
+def playout_nn_population(blobs, precision, number, seed, gid_base=0, gid_model_stride=0, start=None, group_size=0,
+                          want_final=True):
+    """K4 for a population (evolve.py:30-36): blobs is a (M, blob) device tensor of weight images (one row per network);
+    every model plays `number` policy games, all models side by side in one launch per <= num_sms models.
+    -> dict(final i64[M,number], score i32[M,number], moves i32[M,number], group_min i32[M,number/group_size] or None,
+            total_moves i64[1]).  Row m equals playout_nn(blobs[m], ..., gid_base + m*gid_model_stride)."""
+    L.require_cuda()
+    if blobs.dim() != 2 or not blobs.is_contiguous():
+        raise ValueError("blobs must be a contiguous (models, blob) tensor of weight images")
+    d = _dev(blobs)
+    M = blobs.shape[0]
+    r = dict(final=torch.empty((M, number), dtype=torch.int64, device=d) if want_final else None,
+             score=torch.empty((M, number), dtype=torch.int32, device=d),
+             moves=torch.empty((M, number), dtype=torch.int32, device=d),
+             total_moves=torch.zeros(1, dtype=torch.int64, device=d), group_min=None)
+    if group_size > 0:
+        if number % group_size:
+            raise ValueError("number must be a multiple of group_size")
+        r["group_min"] = torch.full((M, number // group_size), 2**31 - 1, dtype=torch.int32, device=d)
+    L.check(L.load_library().b2048_playout_nn_population(
+        L.ctx(d), PRECISIONS[precision], L.ptr(blobs), blobs.stride(0) * blobs.element_size(), M, L.ptr(start), seed, gid_base, gid_model_stride,
+        group_size, L.ptr(r["group_min"]), L.ptr(r["final"]), L.ptr(r["score"]), L.ptr(r["moves"]), L.ptr(r["total_moves"]),
+        number, L.stream_ptr(d)))
+    return r
+
+
 def mcts_nn_lines(blob, precision, origins, number, seed, eval_id_base=0, line_begin=0, line_end=None, per_line=False):
     """mcts_nn.py:4-43 for G origins: legal u8[G,4], rscore i32[G,4], minmov i32[G,4] (INT32_MAX
     where no line was played), lmoves i32[G,4,number] when per_line, total_moves i64[1]."""
@@ -254,3 +280,8 @@ class HostPlayout:
 def set_playout_variant(variant, device=None):
     """K2 kernel variant: 1 (default) legality-first uniform slide, 0 the L,U,D,R attempt cascade."""
     L.check(L.load_library().b2048_set_playout_variant(L.ctx(device), int(variant)))
+
+
+def num_sms(device=None):
+    """SM count of the context's device (persistent kernels launch one CTA per SM)."""
+    return int(L.load_library().b2048_num_sms(L.ctx(device)))

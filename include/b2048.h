@@ -182,6 +182,21 @@ int b2048_playout_nn(b2048_ctx *ctx, int precision, const void *blob, const uint
                      uint64_t gid_base, uint32_t spawn0, int group_size, int32_t *group_min, uint64_t *out_final,
                      uint32_t *out_score, uint32_t *out_moves, uint64_t *move_counter, int64_t n, void *stream);
 
+/* The same policy-game evaluation for every network of a population in ONE launch per <= num_sms models
+ * (evolve.py:30-36 NetworkPopulation.eval calls eval_nn(model, number=eval_num) model after model; 100 games
+ * fill 1 % of a B200, 50 networks side by side fill it).  Every CTA is bound to one model and streams that
+ * model's weight image; work items, spawn streams and results are those of b2048_playout_nn run per model:
+ *   blobs             n_models weight images of `precision`, image m at blobs + m*blob_stride (16-byte multiple)
+ *   gid_model_stride  game id of game j of model m = gid_base + m*gid_model_stride + j (0: common random
+ *                     numbers -- every model plays the same spawn streams)
+ *   start             n_per_model start boards shared by all models, or NULL (fresh boards)
+ *   group_size/group_min, outputs: as b2048_playout_nn, indexed m*n_per_model + j (group_min by
+ *                     (m*n_per_model + j) / group_size; n_per_model must be a multiple of group_size). */
+int b2048_playout_nn_population(b2048_ctx *ctx, int precision, const void *blobs, int64_t blob_stride, int n_models,
+                                const uint64_t *start, uint64_t seed, uint64_t gid_base, uint64_t gid_model_stride,
+                                int group_size, int32_t *group_min, uint64_t *out_final, uint32_t *out_score,
+                                uint32_t *out_moves, uint64_t *move_counter, int64_t n_per_model, void *stream);
+
 /* mcts_nn (mcts_nn.py:4-43) for G origins: lines [line_begin,line_end) of `number` per root move.
  *   out_legal u8[G*4], out_rscore u32[G*4] (root merge score; the reference discards it),
  *   out_lmoves u32[G*4*number] per-line moves at stop (may be NULL; lines stopped early report
