@@ -17,6 +17,6 @@ __all__ = ["B2048Error", "LIB_PATH", "load_library", "engine"]
 def __getattr__(name):
     import importlib
 
-    if name in ("engine", "board", "mcts", "mcts_nn", "eval_nn", "network", "selfplay", "dist", "convnet", "game_dataset", "evolve"):
+    if name in ("engine", "board", "mcts", "mcts_nn", "eval_nn", "network", "selfplay", "dist", "convnet", "game_dataset", "evolve", "trainer", "analysis"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -1,0 +1,116 @@
+"""Analysis harness: the distributions the reference's notebooks are built on --
+`notebooks/distribution.py:11-36` (5000 fixed-order games, play_mcts_fixed games per mode: rows
+[max tile exponent, score, moves]), `distribution2.ipynb` (histograms, Weibull fits of score / moves, max-tile
+percentages) and `compare_models.ipynb` (mean log10(score+1) per model, KS / Welch tests) -- regenerated on the B200
+at sample sizes the Python engine cannot reach (16 M fixed-order games take ~30 ms of kernel time).
+
+Games run in the persistent playout kernels; the per-game reduction (max tile, histogram, fixed-point log-score
+sum) is b2048_game_summary on the device, so a large sweep moves 20 integers to the host, not the games.
+`rows=True` additionally returns the notebooks' per-game array.
+"""
+import argparse
+
+import numpy as np
+import torch
+
+from . import engine
+from .board import _raise_if_flag, _session_seed
+from .network import blob_for
+
+# quality pins published by the reference
+REFERENCE_PINS = {
+    "fixed_mean_log_score": (3.3546, 3.3508),   # compare_models.ipynb:171,1463 (5000 games each)
+    "shipped_mean_log_score": 4.22628,          # compare_models.ipynb:1612 (5000 policy games, 20200213 c64b3)
+    "shipped_frac_2048": 0.240,                 # README.md:30, compare_models.ipynb:1656
+}
+
+
+def summarize(acc):
+    """acc int64[20] from engine.game_summary -> the notebooks' headline numbers."""
+    a = acc.cpu().numpy().astype(np.int64) if torch.is_tensor(acc) else np.asarray(acc, dtype=np.int64)
+    games = int(a[19])
+    hist = {int(2 ** e): int(a[e]) for e in range(1, 16) if a[e]}
+    return dict(games=games, mean_log_score=float(a[16]) / 2.0 ** 40 / max(games, 1), mean_moves=float(a[17]) / max(games, 1),
+                max_score=int(a[18]), maxtile_hist=hist, frac_2048=float(a[11:16].sum()) / max(games, 1))
+
+
+def _collect(play, n, chunk, rows):
+    acc, out = None, []
+    for g0 in range(0, n, chunk):
+        m = min(chunk, n - g0)
+        final, score, moves = play(g0, m)
+        acc, mt = engine.game_summary(final, score, moves, acc, want_maxtile=rows)
+        if rows:
+            out.append(torch.stack([mt.to(torch.int64), score.to(torch.int64) & 0xFFFFFFFF, moves.to(torch.int64)], 1).cpu().numpy())
+    _raise_if_flag()
+    s = summarize(acc)
+    if rows:
+        s["rows"] = np.concatenate(out)  # distribution.py:12-14: [max(get_tiles(board)), score, moves]
+    return s
+
+
+def fixed_distribution(n=5000, seed=None, chunk=1 << 24, rows=False, device="cuda"):
+    """distribution.py:11-14: n fixed-order (L,U,D,R) games from fresh boards."""
+    s = _session_seed(seed)
+    return _collect(lambda g0, m: engine.playout_fixed(m, s, g0, device=device), n, chunk, rows)
+
+
+def policy_distribution(model, n=5000, seed=None, precision=None, chunk=1 << 20, rows=False):
+    """compare_models.ipynb's per-model evaluation (eval_nn.py:4-58 with number=n): n policy games."""
+    blob, prec = blob_for(model, precision)
+    s = _session_seed(seed)
+
+    def play(g0, m):
+        r = engine.playout_nn(blob, prec, m, s, g0)
+        return r["final"], r["score"], r["moves"]
+    return _collect(play, n, chunk, rows)
+
+
+def mcts_distribution(number, times, mode=0, seed=None):
+    """distribution.py:17-36: `times` main games of play_mcts_fixed(number, mode) -> rows [max tile, score, moves]."""
+    from .mcts import play_mcts_fixed
+    from .board import get_tiles
+    s = _session_seed(seed)
+    out = []
+    for g in range(times):
+        board, score, count = play_mcts_fixed(number=number, mode=mode, seed=(s + g) & (2 ** 64 - 1))
+        out.append([max(get_tiles(board)), score, count])
+    return np.array(out)
+
+
+def weibull_fit(x, loc, scale):
+    """distribution2.ipynb: weibull_min.fit(dist, loc=0, scale=mean) for scores, (loc=14, scale=median) for moves."""
+    from scipy.stats import weibull_min
+    return weibull_min.fit(np.asarray(x, dtype=np.float64), loc=loc, scale=scale)
+
+
+def compare(a, b):
+    """compare_models.ipynb stats_test: two-sample KS and Welch t-test."""
+    from scipy import stats
+    return stats.ks_2samp(a, b), stats.ttest_ind(a, b, equal_var=False)
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    p.add_argument("--fixed", type=int, default=5000, help="fixed-order games")
+    p.add_argument("--policy", type=int, default=0, help="policy games of --model")
+    p.add_argument("--model", type=str, default="", help="c64b3 checkpoint (.pt state_dict)")
+    p.add_argument("--precision", type=str, default="fp16")
+    p.add_argument("--seed", type=int, default=12345)
+    p.add_argument("--save", type=str, default="", help="write rows to this .npy (distribution/fixed.npy format)")
+    a = p.parse_args(argv)
+    if a.fixed:
+        s = fixed_distribution(a.fixed, a.seed, rows=bool(a.save))
+        if a.save:
+            np.save(a.save, s.pop("rows"))
+        print("fixed-order:", s, "reference pins (5000 games):", REFERENCE_PINS["fixed_mean_log_score"])
+    if a.policy:
+        from .network import ConvNet
+        m = ConvNet(64, 3, precision=a.precision)
+        m.load_state_dict(torch.load(a.model, map_location="cpu"))
+        s = policy_distribution(m.cuda().eval(), a.policy, a.seed)
+        print("policy:", s, "reference pins:", REFERENCE_PINS["shipped_mean_log_score"], REFERENCE_PINS["shipped_frac_2048"])
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "../../include/b2048.h"
+#include "capi_internal.h"
 #include "engine_kernels.cuh"
 #include "playout_nn.cuh"
 
@@ -13,37 +14,16 @@ using namespace b2048;
 
 static thread_local char g_err[512] = "";
 
-static int fail(const char *what, cudaError_t e) {
+int b2048_fail(const char *what, cudaError_t e) {
     snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
     return 1;
 }
-static int fail_msg(const char *what) {
+int b2048_fail_msg(const char *what) {
     snprintf(g_err, sizeof g_err, "%s", what);
     return 2;
 }
-#define CK(call)                                  \
-    do {                                          \
-        cudaError_t e_ = (call);                  \
-        if (e_ != cudaSuccess) return fail(#call, e_); \
-    } while (0)
-
-#define N_COUNTERS 256
-
-struct b2048_ctx {
-    int device;
-    int num_sms;
-    uint16_t *fin_fwd, *fin_rev;
-    uint32_t *score;
-    uint8_t *moved_fwd, *moved_rev, *legal;
-    uint2 *rowstat;
-    int k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide
-    unsigned long long *counters;  // N_COUNTERS work cursors, one per in-flight launch
-    int *err_flag;
-    unsigned next_counter;
-    // root-search scratch (grown on demand outside of stream capture; see b2048_mcts_fixed)
-    uint64_t *rboard;
-    int64_t rboard_cap;
-};
+#define fail b2048_fail
+#define fail_msg b2048_fail_msg
 
 static Tables tables_of(const b2048_ctx *c) {
     Tables t;
@@ -234,6 +214,16 @@ extern "C" int b2048_soft_targets(b2048_ctx *c, const float *results, float soft
     if (n <= 0) return 0;
     soft_targets_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(results), soft, reinterpret_cast<float4 *>(out), (long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_game_summary(b2048_ctx *c, const uint64_t *finals, const uint32_t *score, const uint32_t *moves,
+                                  uint8_t *out_maxtile, uint64_t *acc20, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    if (!finals || !score || !acc20) return fail_msg("b2048_game_summary: NULL argument");
+    game_summary_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+        (const u64 *)finals, score, moves, out_maxtile, (unsigned long long *)acc20, (long)n);
     CK(cudaGetLastError());
     return 0;
 }

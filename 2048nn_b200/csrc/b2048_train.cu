@@ -1,0 +1,126 @@
+// b2048_train.cu -- extern "C" entry points of the c64b3 training step (trainer.py:14-97), kernels in train.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/b2048.h"
+#include "capi_internal.h"
+#include "train.cuh"
+
+using namespace b2048::train;
+
+static bool g_attr_done[64] = {};
+
+static int ensure_attrs(const b2048_ctx *c) {
+    if (c->device < 64 && g_attr_done[c->device]) return 0;
+    CK(cudaFuncSetAttribute(conv3x3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<64>::BYTES));
+    CK(cudaFuncSetAttribute(conv3x3_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<64>::BYTES));
+    CK(cudaFuncSetAttribute(conv3x3_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<16>::BYTES));
+    CK(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<64>()));
+    CK(cudaFuncSetAttribute(wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<16>()));
+    if (c->device < 64) g_attr_done[c->device] = true;
+    return 0;
+}
+
+extern "C" int64_t b2048_train_workspace_bytes(int64_t max_batch) {
+    if (max_batch <= 0) return 0;
+    return (int64_t)carve(nullptr, max_batch).bytes;
+}
+extern "C" int64_t b2048_train_grad_offset(int64_t max_batch) {
+    if (max_batch <= 0) return -1;
+    return (int64_t)(reinterpret_cast<char *>(carve(nullptr, max_batch).grad) - reinterpret_cast<char *>(0));
+}
+extern "C" int64_t b2048_train_logp_offset(int64_t max_batch) {
+    if (max_batch <= 0) return -1;
+    return (int64_t)(reinterpret_cast<char *>(carve(nullptr, max_batch).logp) - reinterpret_cast<char *>(0));
+}
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, float *bn_buffers, void *workspace,
+                                            int64_t max_batch, const uint64_t *boards, const float *targets, int64_t B,
+                                            float bn_momentum, float *loss_out, void *stream) {
+    if (!params || !bn_buffers || !workspace || !boards || !targets || !loss_out)
+        return b2048_fail_msg("b2048_train_forward_backward: NULL argument");
+    if (B < 2 || B > max_batch) return b2048_fail_msg("b2048_train_forward_backward: need 2 <= B <= max_batch");
+    if (int rc = ensure_attrs(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Workspace w = carve(workspace, max_batch);
+    const long rows = (long)B * 16, n4 = (long)B * 256;
+    const double count = (double)rows;
+    const float eps = 1e-5f;
+    float *run_mean = bn_buffers, *run_var = bn_buffers + 8 * 64;
+    const int ew_grid = cdiv(n4, 256);
+
+    pack_weights_kernel<<<cdiv(7 * 9 * 4096, 256), 256, 0, st>>>(params, w.wf, w.wd);
+    onehot_kernel<<<cdiv(rows, 256), 256, 0, st>>>((const unsigned long long *)boards, w.x0, (long)B);
+    // ---- forward (network.py:78-87 in training mode: BatchNorm uses batch statistics) -----------------------
+    const int conv_grid = cdiv(B, CONV_BOARDS);
+    for (int l = 0; l < NL; l++) {
+        if (l == 0)
+            conv3x3_kernel<16, true><<<conv_grid, CONV_THREADS, ConvSmem<16>::BYTES, st>>>(w.x0, w.wf, w.z[0], w.part, (long)B);
+        else
+            conv3x3_kernel<64, true><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.a[l - 1], w.wf + (size_t)l * 36864,
+                                                                                           w.z[l], w.part, (long)B);
+        bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, conv_grid, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
+                                             run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
+        const float *res = (l >= 2 && (l & 1) == 0) ? w.a[l - 2] : nullptr;
+        bn_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256, (float4 *)w.a[l], n4);
+    }
+    float *stats7 = w.stats + 7 * 256, *coef7 = w.coef + 7 * 128;
+    const int g1 = cdiv(rows, 256) < MAX_PARTS ? cdiv(rows, 256) : MAX_PARTS;
+    head_conv_kernel<<<g1, 256, 0, st>>>(w.a[6], params + P_W7, w.z7, w.part, rows);
+    bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g1, 8, count, params + P_G7, params + P_B7, run_mean + 7 * 64, run_var + 7 * 64,
+                                         bn_momentum, eps, stats7, 4);
+    const int gfc = cdiv(B, 128);
+    if (gfc > MAX_PARTS) return b2048_fail_msg("b2048_train_forward_backward: batch too large for the loss partials");
+    head_fc_kernel<<<gfc, 128, 0, st>>>(w.z7, stats7, params + P_FCW, params + P_FCB, targets, w.h, w.logp, w.dlogits, w.hpart, (long)B);
+    loss_finalize_kernel<<<1, 32, 0, st>>>(w.hpart, gfc, (double)B, loss_out);
+    // ---- backward: head -----------------------------------------------------------------------------------
+    const int g2 = c->num_sms < MAX_PARTS ? c->num_sms : MAX_PARTS;
+    fc_wgrad_kernel<<<g2, 256, 0, st>>>(w.h, w.dlogits, w.hpart, (long)B, cdiv(B, g2));
+    hpart_reduce_kernel<<<cdiv(260, 32), 256, 0, st>>>(w.hpart, g2, 260, w.grad + P_FCW);
+    head_bwd1_kernel<<<g1, 256, 0, st>>>(w.dlogits, params + P_FCW, w.h, w.z7, stats7, w.dy7, w.part, rows);
+    bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g1, 8, count, w.grad + P_G7, w.grad + P_B7, coef7, 4);
+    const int g3 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
+    head_bwd2_kernel<<<g3, 256, 0, st>>>(w.dy7, w.z7, stats7, coef7, params + P_W7, w.a[6], w.da, w.hpart, rows, cdiv(rows, g3));
+    hpart_reduce_kernel<<<cdiv(256, 32), 256, 0, st>>>(w.hpart, g3, 256, w.grad + P_W7);
+    // ---- backward: trunk ----------------------------------------------------------------------------------
+    // a[l2] = relu(bn(z[l2]) + a[l2-2]) for l2 = 2,4,6: dy of a block output (dyA) is also the residual gradient of
+    // the block input, added when that layer's own dy is formed.
+    const int g4 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
+    const int bpc = cdiv(B, WGRAD_SPLITS), splits = cdiv(B, bpc);
+    for (int l = NL - 1; l >= 0; l--) {
+        const bool even = (l & 1) == 0;
+        float *dybuf = even ? w.dyA : w.dyB;
+        const float *gres = (even && l != NL - 1) ? w.dyA : nullptr;
+        bn_bwd_reduce_kernel<<<g4, 256, 0, st>>>((const float4 *)w.da, (const float4 *)gres, (const float4 *)w.a[l],
+                                                 (const float4 *)w.z[l], w.stats + l * 256, (float4 *)dybuf, w.part, rows);
+        bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, w.grad + P_G(l), w.grad + P_B(l), w.coef + l * 128, 64);
+        bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
+                                                     w.coef + l * 128, (float4 *)w.dz, n4);
+        if (l == 0) {
+            wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), st>>>(w.x0, w.dz, w.wpart, (long)B, bpc);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(0), 16);
+        } else {
+            wgrad_kernel<64><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<64>(), st>>>(w.a[l - 1], w.dz, w.wpart, (long)B, bpc);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(l), 64);
+            conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.dz, w.wd + (size_t)l * 36864, w.da,
+                                                                                            nullptr, (long)B);
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2048_train_adam(b2048_ctx *c, float *params, const float *grad, float *adam_m, float *adam_v, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream) {
+    (void)c;
+    if (!params || !grad || !adam_m || !adam_v) return b2048_fail_msg("b2048_train_adam: NULL argument");
+    if (step < 1) return b2048_fail_msg("b2048_train_adam: step counts from 1");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<cdiv(N_PARAMS, 256), 256, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, N_PARAMS, (float)((double)lr / bc1),
+                                                                       beta1, beta2, (float)sqrt(bc2), eps, weight_decay);
+    CK(cudaGetLastError());
+    return 0;
+}

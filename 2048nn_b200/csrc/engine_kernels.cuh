@@ -186,6 +186,58 @@ __global__ void soft_targets_kernel(const float4 *__restrict__ results, float so
     }
 }
 
+// Distribution summary of finished games (notebooks/distribution.py:11-14: [max(get_tiles(board)), score, moves]
+// per game, then histograms / mean log score in the notebooks): per-game max tile exponent, and accumulated into
+// `acc` (integer atomics only -> the result does not depend on scheduling):
+//   acc[0..15]  games by max tile exponent      acc[16] sum of round(log10(score+1) * 2^40)
+//   acc[17]     sum of moves                    acc[18] max score            acc[19] games
+__global__ void __launch_bounds__(256) game_summary_kernel(const u64 *__restrict__ finals, const u32 *__restrict__ score,
+                                                           const u32 *__restrict__ moves, uint8_t *__restrict__ out_maxtile,
+                                                           unsigned long long *__restrict__ acc, long n) {
+    __shared__ unsigned long long s_acc[20];
+    if (threadIdx.x < 20) s_acc[threadIdx.x] = 0ULL;
+    __syncthreads();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    unsigned long long logsum = 0, movsum = 0, games = 0;
+    u32 best = 0;
+    for (; i < n; i += stride) {
+        u64 x = finals[i];
+        // max nibble: fold 16 -> 1 with byte/nibble-wise maxima
+        u32 m = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const u32 t = (u32)(x >> (4 * k)) & 0xFu;
+            m = t > m ? t : m;
+        }
+        if (out_maxtile) out_maxtile[i] = (uint8_t)m;
+        atomicAdd(&s_acc[m], 1ULL);
+        const u32 sc = score[i];
+        logsum += (unsigned long long)__double2ll_rn(ldexp(log10((double)sc + 1.0), 40));
+        movsum += moves ? moves[i] : 0u;
+        best = sc > best ? sc : best;
+        games++;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        logsum += __shfl_xor_sync(0xffffffffu, logsum, o);
+        movsum += __shfl_xor_sync(0xffffffffu, movsum, o);
+        games += __shfl_xor_sync(0xffffffffu, games, o);
+        const u32 ob = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ob > best ? ob : best;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_acc[16], logsum);
+        atomicAdd(&s_acc[17], movsum);
+        atomicMax(&s_acc[18], (unsigned long long)best);
+        atomicAdd(&s_acc[19], games);
+    }
+    __syncthreads();
+    if (threadIdx.x < 20 && s_acc[threadIdx.x]) {
+        if (threadIdx.x == 18) atomicMax(acc + 18, s_acc[18]);
+        else atomicAdd(acc + threadIdx.x, s_acc[threadIdx.x]);
+    }
+}
+
 // root moves of G origins: legal flag, merge score and the moved board (mcts.py:21)
 __global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, long G, uint8_t *__restrict__ legal,
                                   u32 *__restrict__ rscore, u64 *__restrict__ rboard) {

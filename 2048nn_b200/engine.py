@@ -285,3 +285,16 @@ def set_playout_variant(variant, device=None):
 def num_sms(device=None):
     """SM count of the context's device (persistent kernels launch one CTA per SM)."""
     return int(L.load_library().b2048_num_sms(L.ctx(device)))
+
+
+def game_summary(finals, score, moves=None, acc=None, want_maxtile=False):
+    """Accumulate the distribution summary of finished games (b2048_game_summary) into acc (int64[20], created
+    zeroed when None).  -> (acc, maxtile u8[n] or None)"""
+    d = _dev(finals)
+    n = finals.numel()
+    if acc is None:
+        acc = torch.zeros(20, dtype=torch.int64, device=d)
+    mt = torch.empty(n, dtype=torch.uint8, device=d) if want_maxtile else None
+    L.check(L.load_library().b2048_game_summary(L.ctx(d), L.ptr(finals), L.ptr(score), L.ptr(moves), L.ptr(mt), L.ptr(acc), n,
+                                                L.stream_ptr(d)))
+    return acc, mt

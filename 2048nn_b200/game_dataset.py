@@ -25,6 +25,7 @@ class GameDataset(Dataset):
         b = np.ascontiguousarray(np.concatenate(boards).astype(np.uint64))
         r = np.ascontiguousarray(np.concatenate(results))
         d_boards = L.boards_to_device(b)
+        self.packed = d_boards  # uint64 bit patterns (int64 tensor): what the fused training step consumes
         self.boards = engine.encode_boards(d_boards, onehot=self._onehot)
         self.results = engine.soft_targets(torch.from_numpy(r).cuda(), soft)
         if torch.device(device).type != 'cuda':

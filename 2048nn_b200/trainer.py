@@ -1,0 +1,210 @@
+"""Drop-in for the reference's `trainer` module (fqjin/2048NN trainer.py:14-97): supervised training of c64b3 on
+self-play records with KLDivLoss(batchmean) + Adam, evaluated every epoch by `eval_nn_min` (first-death step of
+policy games), best-only checkpoints, patience-based early stopping.
+
+The optimisation step is NOT autograd: `TrainStep` drives the hand-written fp32 CUDA training kernels
+(b2048_train_forward_backward + b2048_train_adam, csrc/train.cuh) on packed uint64 boards; the module's parameters
+and BatchNorm buffers alias flat device vectors the kernels update in place, so `state_dict()` / checkpoints
+keep the reference's 50 keys.  The in-loop evaluation is the tensor-core playout kernel (K4).
+"""
+import argparse
+import random
+from time import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .eval_nn import eval_nn_min
+from .game_dataset import OneHotConvGameDataset
+from .network import ConvNet
+
+N_PARAMS = 231820
+_BN_NAMES = ["in_block.1"] + [f"blocks.{k}.{j}" for k in range(3) for j in (1, 4)] + ["out_block.1"]
+
+
+class TrainStep:
+    """Binds a c64b3 `ConvNet` to the fused training step.
+
+    step(boards, targets) == trainer.py:56-62 (zero_grad, forward in train mode, KLDivLoss(batchmean), backward,
+    Adam step) for one batch: boards int64 (uint64 bit patterns) [B], targets float32 [B,4].  Returns the loss as a
+    0-d device tensor (no host sync)."""
+
+    def __init__(self, model, lr=0.1, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_batch=2048, bn_momentum=0.1):
+        L.require_cuda()
+        if getattr(model, "_shape", (64, 3, 4)) != (64, 3, 4):
+            raise NotImplementedError("the B200 training kernels implement c64b3 = ConvNet(channels=64, blocks=3)")
+        params = list(model.parameters())
+        if sum(p.numel() for p in params) != N_PARAMS:
+            raise ValueError("model is not a c64b3 ConvNet (231,820 parameters)")
+        self.model, self.lr, self.wd, self.betas, self.eps = model, float(lr), float(weight_decay), betas, float(eps)
+        self.max_batch, self.bn_momentum = int(max_batch), float(bn_momentum)
+        dev = params[0].device if params[0].device.type == "cuda" else torch.device("cuda")
+        self.device = dev
+        # flat parameter / buffer vectors; the module's tensors become views of them
+        self.params = torch.empty(N_PARAMS, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.params[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.params[off:off + n].view(p.shape)
+                off += n
+            self.bn = torch.zeros(2 * 8 * 64, dtype=torch.float32, device=dev)
+            mods = dict(model.named_modules())
+            self._bn_mods = [mods[n] for n in _BN_NAMES]
+            for i, bn in enumerate(self._bn_mods):
+                c = bn.running_mean.numel()
+                self.bn[i * 64:i * 64 + c].copy_(bn.running_mean)
+                self.bn[512 + i * 64:512 + i * 64 + c].copy_(bn.running_var)
+                bn.running_mean = self.bn[i * 64:i * 64 + c]
+                bn.running_var = self.bn[512 + i * 64:512 + i * 64 + c]
+            self._nbt = torch.stack([bn.num_batches_tracked.to(dev) for bn in self._bn_mods]).contiguous()
+            for i, bn in enumerate(self._bn_mods):
+                bn.num_batches_tracked = self._nbt[i]
+        self.m = torch.zeros(N_PARAMS, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(N_PARAMS, dtype=torch.float32, device=dev)
+        lib = L.load_library()
+        nbytes = lib.b2048_train_workspace_bytes(self.max_batch)
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        g0 = lib.b2048_train_grad_offset(self.max_batch)
+        self.grad = self.workspace[g0:g0 + 4 * N_PARAMS].view(torch.float32)
+        l0 = lib.b2048_train_logp_offset(self.max_batch)
+        self._logp = self.workspace[l0:l0 + 16 * self.max_batch].view(torch.float32).view(-1, 4)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.steps = 0
+
+    def forward_backward(self, boards, targets):
+        """Loss and gradient of one batch (BatchNorm running statistics are updated as in train mode)."""
+        B = boards.numel()
+        boards, targets = boards.contiguous(), targets.contiguous()
+        if targets.shape != (B, 4) or targets.dtype != torch.float32 or boards.dtype != torch.int64:
+            raise ValueError("boards: int64 [B], targets: float32 [B,4]")
+        L.check(L.load_library().b2048_train_forward_backward(
+            L.ctx(self.device), L.ptr(self.params), L.ptr(self.bn), L.ptr(self.workspace), self.max_batch, L.ptr(boards),
+            L.ptr(targets), B, self.bn_momentum, L.ptr(self.loss), L.stream_ptr(self.device)))
+        self._nbt += 1
+        self._invalidate_weight_images()
+        return self.loss[0]
+
+    def _invalidate_weight_images(self):
+        # the kernels write parameters / running statistics behind autograd's version counters: drop the cached
+        # inference weight images (network.ConvNet.blob, network.blob_for) so the next playout re-folds them
+        self.model.__dict__["_blob_key"] = None
+        self.model.__dict__.pop("_b2048_blobs", None)
+
+    def log_probs(self, B):
+        """log-probabilities the last forward_backward computed for its batch (train-mode forward)."""
+        return self._logp[:B]
+
+    def adam(self, grad=None):
+        self.steps += 1
+        g = self.grad if grad is None else grad
+        L.check(L.load_library().b2048_train_adam(L.ctx(self.device), L.ptr(self.params), L.ptr(g), L.ptr(self.m), L.ptr(self.v),
+                                                  self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.steps,
+                                                  L.stream_ptr(self.device)))
+        self._invalidate_weight_images()
+
+    def step(self, boards, targets):
+        loss = self.forward_backward(boards, targets)
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.grad)  # data parallel: mean gradient over ranks
+            self.grad /= torch.distributed.get_world_size()
+        self.adam()
+        return loss
+
+
+def train_epoch(stepper, boards, targets, batch_size, generator=None):
+    """One shuffled pass (DataLoader(shuffle=True), trainer.py:29,55): returns the mean batch loss as a float."""
+    n = boards.numel()
+    perm = torch.randperm(n, device=boards.device, generator=generator)
+    total = torch.zeros((), dtype=torch.float32, device=boards.device)
+    batches = 0
+    for i in range(0, n, batch_size):
+        idx = perm[i:i + batch_size]
+        if idx.numel() < 2:
+            break
+        total += stepper.step(boards[idx], targets[idx])
+        batches += 1
+    return float(total.item()) / max(batches, 1), batches
+
+
+def main(args):
+    """trainer.py:14-97."""
+    if args.name:
+        args.name += '_'
+    logname = f'{args.name}{args.t_tuple[0]}_{args.t_tuple[1]}_soft{args.soft}' \
+              f'c{args.channels}b{args.blocks}_p{args.patience}_' \
+              f'bs{args.batch_size}lr{args.lr}d{args.decay}_s{args.seed}'
+    print(logname)
+    random.seed(args.seed)
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    L.require_cuda()
+    device = torch.device('cuda')
+    print('Using {}'.format(device))
+
+    train_set = OneHotConvGameDataset(args.path, args.t_tuple[0], args.t_tuple[1], device, soft=args.soft)
+    m = ConvNet(channels=args.channels, blocks=args.blocks, precision="fp16")
+    if args.pretrained:
+        m.load_state_dict(torch.load('models/{}.pt'.format(args.pretrained), map_location=device))
+        print('Loaded ' + args.pretrained)
+        logname = 'pre_' + logname
+    m.to(device)
+    stepper = TrainStep(m, lr=args.lr, weight_decay=args.decay, max_batch=args.batch_size)
+    t_loss, min_move = [], []
+    best, timer = 0.0, 0
+    stop = args.epochs if args.patience == 0 else args.patience
+    for epoch in range(args.epochs):
+        print('-' * 10)
+        print('Epoch: {}'.format(epoch))
+        timer += 1
+        m.train()
+        running_loss, _ = train_epoch(stepper, train_set.packed, train_set.results, args.batch_size)
+        if epoch == 2 and running_loss > 210 / 1000:
+            stop = 0
+        print('Train mLoss: {:.3f}'.format(1e3 * running_loss))
+        t_loss.append(running_loss)
+
+        m.eval()
+        time1 = time()
+        ave_min_move = eval_nn_min(m, number=10, repeats=40, device=device)
+        time_str = ', took {:.0f} seconds'.format(time() - time1)
+        min_move.append(ave_min_move)
+        if ave_min_move >= best:
+            print(str(ave_min_move) + ' ** Best' + time_str)
+            best, timer = ave_min_move, 0
+            torch.save(m.state_dict(), 'models/' + logname + '_best.pt')
+        else:
+            print(str(ave_min_move) + time_str)
+        if timer >= stop:
+            print('Ran out of patience')
+            print(f'Best score: {best}')
+            break
+        else:
+            print(f'{stop - timer} epochs remaining')
+    np.savez('logs/' + logname, t_loss=t_loss, min_move=min_move, params=args)
+    return t_loss, min_move
+
+
+def parser():
+    p = argparse.ArgumentParser()
+    p.add_argument('--path', type=str, default='selfplay/', help='path to training data with prefix')
+    p.add_argument('--t_tuple', type=int, nargs=2, default=(20, 200), help='tuple for training data range')
+    p.add_argument('--channels', type=int, default=64)
+    p.add_argument('--blocks', type=int, default=3)
+    p.add_argument('--epochs', type=int, default=1000)
+    p.add_argument('--patience', type=int, default=10,
+                   help='Early stopping based on log score eval. If zero, no early stopping.')
+    p.add_argument('--batch_size', type=int, default=2048)
+    p.add_argument('--lr', type=float, default=0.1)
+    p.add_argument('--decay', type=float, default=0.0)
+    p.add_argument('--soft', type=float, default=3.0)
+    p.add_argument('--name', type=str, default='', help='Additional prepend output name')
+    p.add_argument('--seed', type=int, default=0)
+    p.add_argument('--pretrained', type=str, default='', help='Path to network to continue training')
+    return p
+
+
+if __name__ == '__main__':
+    main(parser().parse_args())

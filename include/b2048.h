@@ -110,6 +110,14 @@ int b2048_encode_boards(b2048_ctx *ctx, const uint64_t *boards, int mode, float 
  * (game_dataset.py:25-28).  results, out: float32[N*4]. */
 int b2048_soft_targets(b2048_ctx *ctx, const float *results, float soft, float *out, int64_t n, void *stream);
 
+/* Distribution summary of n finished games (notebooks/distribution.py:11-14 rows [max tile exponent, score, moves]
+ * and the notebooks' histograms / mean log score), ACCUMULATED into acc20 (caller zeroes it):
+ *   acc20[0..15] games by max tile exponent, [16] sum of round(log10(score+1) * 2^40), [17] sum of moves,
+ *   [18] max score, [19] games.  Integer atomics only: independent of scheduling and of how games are sharded
+ *   (ranks add their acc20 vectors, MAX for [18]).  out_maxtile u8[n] and moves may be NULL. */
+int b2048_game_summary(b2048_ctx *ctx, const uint64_t *finals, const uint32_t *score, const uint32_t *moves,
+                       uint8_t *out_maxtile, uint64_t *acc20, int64_t n, void *stream);
+
 /* raw stream words for parity tests: out[g*count + j] = draw(first + j) of stream (seed, gid_base+g) */
 int b2048_rng_draws(b2048_ctx *ctx, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
                     uint64_t *out, int64_t n, void *stream);
@@ -207,6 +215,31 @@ int b2048_mcts_nn(b2048_ctx *ctx, int precision, const void *blob, const uint64_
                   int line_begin, int line_end, uint64_t seed, uint64_t eval_id_base, uint8_t *out_legal,
                   uint32_t *out_rscore, uint32_t *out_lmoves, int32_t *out_minmov, uint64_t *move_counter,
                   void *stream);
+
+/* ---- c64b3 training step (trainer.py:14-97) -------------------------------------------------
+ * One optimisation step of trainer.py:55-62 -- m(x) in train mode (BatchNorm batch statistics, running-stat
+ * update), KLDivLoss(reduction='batchmean') against soft targets, backward, Adam -- in fp32, hand-written
+ * (no autograd / cuDNN).  Flat fp32 vectors, `parameters()` order of network.py:43-76:
+ *   params[231820]   in_block conv [64][16][3][3], BN weight, BN bias; 3 x (conv, BN w, BN b, conv, BN w, BN b);
+ *                    out_block conv [4][64], BN w[4], BN b[4]; policy weight [4][64], bias [4]
+ *   bn_buffers[1024] running_mean [8 BN layers][64] then running_var [8][64] (out_block BN: first 4 of its 64)
+ *   adam_m, adam_v   [231820] first / second moment
+ * workspace: caller-allocated device memory of b2048_train_workspace_bytes(max_batch) bytes (no hidden
+ * allocation); after forward_backward it holds the gradient (float[231820] at b2048_train_grad_offset) and the
+ * batch's log-probabilities (float[B*4] at b2048_train_logp_offset).
+ * forward_backward: boards u64[B] (the one-hot encoder of game_dataset.py:46-48 is fused), targets f32[B*4];
+ *   loss_out device float[1].  Deterministic: batch reductions are summed in a fixed order.
+ * adam: torch.optim.Adam's update (L2 weight decay added to the gradient, bias correction, eps outside the
+ *   square root) for 1-based `step`.  Kept separate so that data-parallel ranks can allreduce the gradient
+ *   between the two calls. */
+int64_t b2048_train_workspace_bytes(int64_t max_batch);
+int64_t b2048_train_grad_offset(int64_t max_batch);
+int64_t b2048_train_logp_offset(int64_t max_batch);
+int b2048_train_forward_backward(b2048_ctx *ctx, const float *params, float *bn_buffers, void *workspace,
+                                 int64_t max_batch, const uint64_t *boards, const float *targets, int64_t B,
+                                 float bn_momentum, float *loss_out, void *stream);
+int b2048_train_adam(b2048_ctx *ctx, float *params, const float *grad, float *adam_m, float *adam_v, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream);
 
 #ifdef __cplusplus
 }
