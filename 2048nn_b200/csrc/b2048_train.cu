@@ -113,14 +113,16 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     return 0;
 }
 
-extern "C" int b2048_train_adam(b2048_ctx *c, float *params, const float *grad, float *adam_m, float *adam_v, float lr,
-                                float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream) {
+extern "C" int b2048_train_adam(b2048_ctx *c, float *params, const float *grad, float *adam_m, float *adam_v, double lr,
+                                double beta1, double beta2, double eps, double weight_decay, int64_t step, void *stream) {
     (void)c;
     if (!params || !grad || !adam_m || !adam_v) return b2048_fail_msg("b2048_train_adam: NULL argument");
     if (step < 1) return b2048_fail_msg("b2048_train_adam: step counts from 1");
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    adam_kernel<<<cdiv(N_PARAMS, 256), 256, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, N_PARAMS, (float)((double)lr / bc1),
-                                                                       beta1, beta2, (float)sqrt(bc2), eps, weight_decay);
+    // scalars are formed in double and rounded once, as torch.optim.Adam does with its Python floats
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    adam_kernel<<<cdiv(N_PARAMS, 256), 256, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, N_PARAMS, (float)(lr / bc1),
+                                                                       (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                                       (float)sqrt(bc2), (float)eps, (float)weight_decay);
     CK(cudaGetLastError());
     return 0;
 }

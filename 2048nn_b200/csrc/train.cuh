@@ -740,13 +740,14 @@ __global__ void __launch_bounds__(256) head_bwd2_kernel(const float *__restrict_
 
 // ---- Adam (trainer.py:36-38 torch.optim.Adam(lr, weight_decay): L2 added to the gradient, bias-corrected) ------
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                            int n, float lr_over_bc1, float beta1, float beta2, float sqrt_bc2, float eps, float wd) {
+                            int n, float lr_over_bc1, float one_minus_beta1, float beta2, float one_minus_beta2, float sqrt_bc2,
+                            float eps, float wd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float w = p[i];
     const float gr = fmaf(wd, w, g[i]);
-    const float mm = m[i] + (gr - m[i]) * (1.f - beta1);           // exp_avg.lerp_(grad, 1 - beta1)
-    const float vv = fmaf(1.f - beta2, gr * gr, beta2 * v[i]);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float mm = m[i] + (gr - m[i]) * one_minus_beta1;          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vv = fmaf(one_minus_beta2, gr * gr, beta2 * v[i]);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     m[i] = mm, v[i] = vv;
     p[i] = w - lr_over_bc1 * (mm / (sqrtf(vv) / sqrt_bc2 + eps));
 }

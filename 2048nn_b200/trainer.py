@@ -30,7 +30,8 @@ class TrainStep:
     Adam step) for one batch: boards int64 (uint64 bit patterns) [B], targets float32 [B,4].  Returns the loss as a
     0-d device tensor (no host sync)."""
 
-    def __init__(self, model, lr=0.1, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_batch=2048, bn_momentum=0.1):
+    def __init__(self, model, lr=0.1, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_batch=2048, bn_momentum=0.1,
+                 use_graph=True):
         L.require_cuda()
         if getattr(model, "_shape", (64, 3, 4)) != (64, 3, 4):
             raise NotImplementedError("the B200 training kernels implement c64b3 = ConvNet(channels=64, blocks=3)")
@@ -73,6 +74,11 @@ class TrainStep:
         self._logp = self.workspace[l0:l0 + 16 * self.max_batch].view(torch.float32).view(-1, 4)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.steps = 0
+        # the ~65 launches of forward+backward replay as one CUDA graph per batch size (static input buffers)
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        self._in_boards = torch.zeros(self.max_batch, dtype=torch.int64, device=dev)
+        self._in_targets = torch.zeros((self.max_batch, 4), dtype=torch.float32, device=dev)
 
     def forward_backward(self, boards, targets):
         """Loss and gradient of one batch (BatchNorm running statistics are updated as in train mode)."""
@@ -80,9 +86,23 @@ class TrainStep:
         boards, targets = boards.contiguous(), targets.contiguous()
         if targets.shape != (B, 4) or targets.dtype != torch.float32 or boards.dtype != torch.int64:
             raise ValueError("boards: int64 [B], targets: float32 [B,4]")
-        L.check(L.load_library().b2048_train_forward_backward(
-            L.ctx(self.device), L.ptr(self.params), L.ptr(self.bn), L.ptr(self.workspace), self.max_batch, L.ptr(boards),
-            L.ptr(targets), B, self.bn_momentum, L.ptr(self.loss), L.stream_ptr(self.device)))
+        if B > self.max_batch:
+            raise ValueError("batch larger than max_batch")
+        if not self.use_graph:
+            self._enqueue(boards, targets, B)
+        else:
+            self._in_boards[:B].copy_(boards)
+            self._in_targets[:B].copy_(targets)
+            g = self._graphs.get(B)
+            if g is None:
+                self._enqueue(self._in_boards, self._in_targets, B)  # eager once: also the capture warm-up
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(self._in_boards, self._in_targets, B)
+                self._graphs[B] = g  # (capturing records the launches, it does not run them)
+            else:
+                g.replay()
         self._nbt += 1
         self._invalidate_weight_images()
         return self.loss[0]
@@ -92,6 +112,11 @@ class TrainStep:
         # inference weight images (network.ConvNet.blob, network.blob_for) so the next playout re-folds them
         self.model.__dict__["_blob_key"] = None
         self.model.__dict__.pop("_b2048_blobs", None)
+
+    def _enqueue(self, boards, targets, B):
+        L.check(L.load_library().b2048_train_forward_backward(
+            L.ctx(self.device), L.ptr(self.params), L.ptr(self.bn), L.ptr(self.workspace), self.max_batch, L.ptr(boards),
+            L.ptr(targets), B, self.bn_momentum, L.ptr(self.loss), L.stream_ptr(self.device)))
 
     def log_probs(self, B):
         """log-probabilities the last forward_backward computed for its batch (train-mode forward)."""

@@ -238,8 +238,8 @@ int64_t b2048_train_logp_offset(int64_t max_batch);
 int b2048_train_forward_backward(b2048_ctx *ctx, const float *params, float *bn_buffers, void *workspace,
                                  int64_t max_batch, const uint64_t *boards, const float *targets, int64_t B,
                                  float bn_momentum, float *loss_out, void *stream);
-int b2048_train_adam(b2048_ctx *ctx, float *params, const float *grad, float *adam_m, float *adam_v, float lr,
-                     float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream);
+int b2048_train_adam(b2048_ctx *ctx, float *params, const float *grad, float *adam_m, float *adam_v, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, int64_t step, void *stream);
 
 #ifdef __cplusplus
 }
