@@ -259,6 +259,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout at VERSION/INFO: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("2048nn_b200")
     eng = pkg.engine
