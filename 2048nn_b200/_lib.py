@@ -47,6 +47,7 @@ _SIGS = {
     "b2048_playout_nn": (C.c_int, [P, C.c_int, P, P, u64, u64, u32, C.c_int, P, P, P, P, P, i64, P]),
     "b2048_playout_nn_population": (C.c_int, [P, C.c_int, P, i64, C.c_int, P, u64, u64, u64, C.c_int, P, P, P, P, P, i64, P]),
     "b2048_mcts_nn": (C.c_int, [P, C.c_int, P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P]),
+    "b2048_selfplay_fixed": (C.c_int, [P, P, i64, u64, u64, C.c_int, C.c_int, C.c_int, u64, C.c_int, P, P, P, P, P, P, P, P]),
     "b2048_game_summary": (C.c_int, [P, P, P, P, P, P, i64, P]),
     "b2048_train_workspace_bytes": (i64, [i64]),
     "b2048_train_grad_offset": (i64, [i64]),

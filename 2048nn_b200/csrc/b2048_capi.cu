@@ -9,6 +9,7 @@
 #include "capi_internal.h"
 #include "engine_kernels.cuh"
 #include "playout_nn.cuh"
+#include "selfplay_kernels.cuh"
 
 using namespace b2048;
 
@@ -304,6 +305,44 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
     p.out_count = out_count;
     p.out_minmov = out_minmov;
     return launch_playout(c, p, st);
+}
+
+extern "C" int b2048_selfplay_fixed(b2048_ctx *c, const uint64_t *starts, int64_t G, uint64_t game_id_base,
+                                    uint64_t games_total, int number, int times, int mode, uint64_t seed, int max_steps,
+                                    uint64_t *out_boards, float *out_results, uint64_t *out_final, int64_t *out_score,
+                                    int32_t *out_steps, int32_t *out_status, uint64_t *move_counter, void *stream) {
+    if (G <= 0) return 0;
+    if (number <= 0 || times <= 0 || times > SELFPLAY_MAX_TIMES || max_steps <= 0)
+        return fail_msg("b2048_selfplay_fixed: need number > 0, 1 <= times <= 64, max_steps > 0");
+    if (mode != B2048_MODE_MEANLOG && mode != B2048_MODE_MEDIAN && mode != B2048_MODE_MIN)
+        return fail_msg("b2048_selfplay_fixed: unknown mode");
+    if (mode != B2048_MODE_MIN && times != 1) return fail_msg("b2048_selfplay_fixed: times > 1 is defined for the min mode only");
+    if (mode == B2048_MODE_MEDIAN && number > 2048) return fail_msg("b2048_selfplay_fixed: median mode supports number <= 2048");
+    if (!out_final || !out_score || !out_steps || !out_status) return fail_msg("b2048_selfplay_fixed: NULL output");
+    if (games_total < game_id_base + (uint64_t)G) return fail_msg("b2048_selfplay_fixed: games_total < game_id_base + G");
+    SelfplayParams p;
+    memset(&p, 0, sizeof p);
+    p.tb = tables_of(c);
+    p.starts = (const u64 *)starts;
+    p.G = (long)G;
+    p.g0 = game_id_base;
+    p.g_total = games_total;
+    p.number = number, p.times = times, p.mode = mode, p.max_steps = max_steps;
+    p.seed = seed;
+    p.out_boards = (u64 *)out_boards;
+    p.out_results = out_results;
+    p.out_final = (u64 *)out_final;
+    p.out_score = (long long *)out_score;
+    p.out_steps = out_steps;
+    p.out_status = out_status;
+    p.move_counter = (unsigned long long *)move_counter;
+    p.err_flag = c->err_flag;
+    long lines = (long)times * 4 * number;
+    int threads = (int)(lines < 1024 ? ((lines + 31) / 32) * 32 : 1024);
+    size_t smem = mode == B2048_MODE_MEDIAN ? (size_t)16 * number : 0;
+    selfplay_fixed_kernel<<<(unsigned)G, threads, smem, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

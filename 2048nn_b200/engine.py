@@ -298,3 +298,23 @@ def game_summary(finals, score, moves=None, acc=None, want_maxtile=False):
     L.check(L.load_library().b2048_game_summary(L.ctx(d), L.ptr(finals), L.ptr(score), L.ptr(moves), L.ptr(mt), L.ptr(acc), n,
                                                 L.stream_ptr(d)))
     return acc, mt
+
+
+def selfplay_fixed_games(G, number, seed, times=1, mode=2, starts=None, game_id_base=0, games_total=None, max_steps=4096,
+                         record=True, device="cuda"):
+    """Whole fixed-order root-search main games on the device (b2048_selfplay_fixed): one CTA per game.
+    -> dict(boards i64[G,max_steps], results f32[G,max_steps,4] (record=True), final i64[G], score i64[G], steps i32[G],
+            status i32[G] (1 = stopped at max_steps), total_moves i64[1])"""
+    L.require_cuda()
+    d = torch.device(device) if starts is None else _dev(starts)
+    games_total = game_id_base + G if games_total is None else games_total
+    r = dict(boards=torch.empty((G, max_steps), dtype=torch.int64, device=d) if record else None,
+             results=torch.empty((G, max_steps, 4), dtype=torch.float32, device=d) if record else None,
+             final=torch.empty(G, dtype=torch.int64, device=d), score=torch.empty(G, dtype=torch.int64, device=d),
+             steps=torch.empty(G, dtype=torch.int32, device=d), status=torch.empty(G, dtype=torch.int32, device=d),
+             total_moves=torch.zeros(1, dtype=torch.int64, device=d))
+    L.check(L.load_library().b2048_selfplay_fixed(
+        L.ctx(d), L.ptr(starts), G, game_id_base, games_total, number, times, mode, seed, max_steps, L.ptr(r["boards"]),
+        L.ptr(r["results"]), L.ptr(r["final"]), L.ptr(r["score"]), L.ptr(r["steps"]), L.ptr(r["status"]),
+        L.ptr(r["total_moves"]), L.stream_ptr(d)))
+    return r

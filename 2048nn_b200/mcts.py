@@ -63,7 +63,31 @@ def mcts_fixed_min(origin, number=10, seed=None, eval_id=0):
 
 
 def play_mcts_fixed(board=None, number=10, press_enter=False, mode=0, seed=None):
-    """mcts.py:106-148: play a game choosing argmax of mcts_fixed / _moves / _min each move."""
+    """mcts.py:106-148: play a game choosing argmax of mcts_fixed / _moves / _min each move.
+
+    The whole main game runs inside one kernel launch (b2048_selfplay_fixed: one CTA, no host round trip per main
+    move) on the same spawn streams as the step-by-step loop below, which remains the interactive
+    (`press_enter`) path.  Mode 0 compares fixed-point (2^-40) log-score means on the device where the loop uses
+    NumPy's float64 mean: the two can only disagree when two root values differ by less than ~1e-11."""
+    s = _session_seed(seed)
+    if press_enter:
+        return _play_mcts_fixed_host(board, number, True, mode, s)
+    if mode not in (0, 1, 2):
+        raise KeyError(mode)
+    start = None if not board else _dev([board])
+    max_steps = 8192
+    while True:
+        r = engine.selfplay_fixed_games(1, int(number), s, times=1, mode=int(mode), starts=start, max_steps=max_steps,
+                                        record=False)
+        _raise_if_flag()
+        if int(r["status"].item()) == 0:
+            break
+        max_steps *= 8  # the game outlived the step budget: replay it with a larger one
+    return int(_board._host(r["final"])[0]), int(r["score"].item()), int(r["steps"].item())
+
+
+def _play_mcts_fixed_host(board=None, number=10, press_enter=False, mode=0, seed=None):
+    """The reference's loop shape: one root evaluation (kernel launch) per main move, decision on the host."""
     s = _session_seed(seed)
     if not board:
         board = _board.generate_init_tiles(s, 0)

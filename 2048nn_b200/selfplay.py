@@ -13,7 +13,7 @@ import torch
 
 from . import dist as _dist
 from . import engine
-from .board import _session_seed
+from .board import _raise_if_flag, _session_seed
 from .network import blob_for
 
 
@@ -28,7 +28,68 @@ def selfplay_batch(G, number=10, model=None, times=1, seed=None, precision=None,
     mcts_fixed_min averaged over `times` (selfplay.py:9-59); else NN-policy mcts_nn (selfplay.py:62-115).
 
     Returns a list of G records dict(boards uint64[T], results float32[T,4], score int) and the
-    total number of playout moves (all ranks)."""
+    total number of playout moves (all ranks).
+
+    Fixed-order games run device-resident (one CTA per main game, b2048_selfplay_fixed), main games sharded over the
+    process group; NN-policy games advance in lock-step with lines sharded (`_selfplay_batch_steps`).  Both give the
+    same games for every world size."""
+    if model is None and times <= 64:
+        return _selfplay_fixed_device(G, number, times, _session_seed(seed), starts, max_steps, group)
+    return _selfplay_batch_steps(G, number, model, times, seed, precision, starts, max_steps, group)
+
+
+def _selfplay_fixed_device(G, number, times, s, starts, max_steps, group):
+    import torch.distributed as td
+    dev = torch.device("cuda")
+    world = td.get_world_size(group) if td.is_available() and td.is_initialized() else 1
+    rank = td.get_rank(group) if world > 1 else 0
+    per = (G + world - 1) // world
+    g0 = min(G, rank * per)
+    n_local = max(0, min(G, g0 + per) - g0)
+    budget = int(min(max_steps, 4096))
+    while True:
+        r = None
+        if n_local:
+            st = None if starts is None else starts.to(dev)[g0:g0 + n_local].contiguous()
+            r = engine.selfplay_fixed_games(n_local, int(number), s, times=int(times), mode=2, starts=st, game_id_base=g0,
+                                            games_total=G, max_steps=budget)
+        _raise_if_flag()
+        clipped = torch.zeros(1, dtype=torch.int32, device=dev)
+        if r is not None:
+            clipped += (r["status"] != 0).any().to(torch.int32)
+        if world > 1:
+            td.all_reduce(clipped, op=td.ReduceOp.MAX, group=group)
+        if not int(clipped.item()) or budget >= max_steps:
+            break
+        budget = int(min(max_steps, budget * 8))  # some game outlived the step budget: replay with a larger one
+    # gather the shards (padded to `per` games) so that every rank returns all G records
+    def padded(t, shape, dtype):
+        out = torch.zeros((per,) + shape, dtype=dtype, device=dev)
+        if n_local:
+            out[:n_local] = t
+        return out
+    steps = padded(r["steps"] if r else None, (), torch.int32)
+    score = padded(r["score"] if r else None, (), torch.int64)
+    boards = padded(r["boards"] if r else None, (budget,), torch.int64)
+    results = padded(r["results"] if r else None, (budget, 4), torch.float32)
+    moves = r["total_moves"].clone() if r else torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:
+        def gather(t):
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+            td.all_gather_into_tensor(out, t.contiguous(), group=group)
+            return out.reshape((world * per,) + tuple(t.shape[1:]))
+        steps, score, boards, results = gather(steps), gather(score), gather(boards), gather(results)
+        td.all_reduce(moves, group=group)
+    hs, hsc = steps.cpu().numpy(), score.cpu().numpy()
+    hb, hr = boards.cpu().numpy().view(np.uint64), results.cpu().numpy()
+    records = [dict(boards=hb[g, :hs[g]].copy(), results=hr[g, :hs[g]].copy(), score=int(hsc[g])) for g in range(G)]
+    return records, int(moves.item())
+
+
+def _selfplay_batch_steps(G, number=10, model=None, times=1, seed=None, precision=None, starts=None, max_steps=100000,
+                          group=None):
+    """Lock-step main games: every main step is one root-evaluation launch for all G games (lines sharded over the
+    ranks, one [G,4] allreduce) plus tiny device ops; the host reads one scalar per main step."""
     s = _session_seed(seed)
     dev = torch.device("cuda")
     boards = engine.init_boards(G, s, 0, device=dev) if starts is None else starts.to(dev).clone()

@@ -409,6 +409,19 @@ def main():
                          "note": "15.2 MFLOP of in-bounds convolution work per sample vs 148 SM x 128 FMA/clk (FFMA2) at max clock; "
                                  "the reference's step is PyTorch eager: 3.5 ms fp32 / 2.2 ms TF32 on the same GPU (tools/train_bench.py)"},
         }
+    # BASELINE config[0]: one full play_mcts_fixed(number=10) main game from a fresh board (device-resident kernel)
+    import time as _time
+    pkg.mcts.play_mcts_fixed(number=10, seed=1)
+    torch.cuda.synchronize()
+    t0w = _time.perf_counter()
+    games = [pkg.mcts.play_mcts_fixed(number=10, seed=sd) for sd in (12345, 2, 3)]
+    torch.cuda.synchronize()
+    dtw = _time.perf_counter() - t0w
+    line["mcts_fixed_game"] = {
+        "workload": "play_mcts_fixed(number=10, mode=0): 3 full main games from fresh boards, one kernel launch each, wall clock",
+        "ms_per_game": dtw / 3 * 1e3, "main_moves": [g[2] for g in games], "scores": [g[1] for g in games],
+        "us_per_main_move": dtw * 1e6 / sum(g[2] for g in games),
+        "reference": "9.56 s per game for the Python reference (BASELINE.md, survey container CPU)"}
     cores = os.cpu_count() or 1
     if world == 1:
         v, sample = cpu_port_rate(args.cpu_seconds, cores)

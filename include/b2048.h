@@ -216,6 +216,23 @@ int b2048_mcts_nn(b2048_ctx *ctx, int precision, const void *blob, const uint64_
                   uint32_t *out_rscore, uint32_t *out_lmoves, int32_t *out_minmov, uint64_t *move_counter,
                   void *stream);
 
+/* Whole main games of the fixed-order root search on the device: play_mcts_fixed (mcts.py:106-148; modes
+ * B2048_MODE_MEANLOG / MEDIAN / MIN = mcts_fixed / mcts_fixed_moves / mcts_fixed_min) and selfplay_fixed
+ * (selfplay.py:9-59: MIN mode averaged over `times` evaluations).  One CTA per main game, no host round trip per
+ * main move; the streams are those of b2048_mcts_fixed + b2048_spawn_batch driven by the host loop, so the games are
+ * identical:  main game m = game_id_base + g: start board / main spawns from stream (seed, m); evaluation t at main
+ * step s has eval_id = (s*times + t + 1)*games_total + m.  games_total = games of the whole session (ranks play
+ * disjoint [game_id_base, game_id_base+G) ranges of it).
+ *   starts        G start boards or NULL; 0 entry -> fresh board
+ *   out_boards    u64[G*max_steps] board before each main move (may be NULL), out_results f32[G*max_steps*4] the
+ *                 root values it was chosen from (may be NULL): the npz record of selfplay.py:55-58
+ *   out_final/out_score/out_steps [G]; out_status[G]: 0 game over, 1 stopped because max_steps was reached
+ *   move_counter  optional u64[1], += playout moves played */
+int b2048_selfplay_fixed(b2048_ctx *ctx, const uint64_t *starts, int64_t G, uint64_t game_id_base, uint64_t games_total,
+                         int number, int times, int mode, uint64_t seed, int max_steps, uint64_t *out_boards,
+                         float *out_results, uint64_t *out_final, int64_t *out_score, int32_t *out_steps,
+                         int32_t *out_status, uint64_t *move_counter, void *stream);
+
 /* ---- c64b3 training step (trainer.py:14-97) -------------------------------------------------
  * One optimisation step of trainer.py:55-62 -- m(x) in train mode (BatchNorm batch statistics, running-stat
  * update), KLDivLoss(reduction='batchmean') against soft targets, backward, Adam -- in fp32, hand-written
