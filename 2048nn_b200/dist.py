@@ -1,8 +1,10 @@
 """Multi-GPU sharding of root evaluations: one process per GPU, torch.distributed over NCCL.
 
-Playouts are independent, so a root evaluation shards by LINES: rank r plays lines
-[begin_r, end_r) of every (origin, root move) with the same (seed, eval_id) keyed streams, and
-the ranks combine their partial statistics with ONE small allreduce:
+Playouts are independent, so a root evaluation shards over the ranks with the same (seed, eval_id) keyed
+streams -- by ORIGINS when there are at least as many origins as ranks (config 4: every rank evaluates whole
+(origin, root move) groups, so the early stop of the min-move search prunes exactly as on one GPU), else by LINES
+(config 3: rank r plays lines [begin_r, end_r) of every group) -- and the ranks combine their partial statistics
+with ONE small allreduce:
 
     mean-log (mcts.py:4-34)      logsum i64[G,4] fixed-point + count i32[G,4]   SUM
     min-move (mcts.py:73-103,
@@ -31,6 +33,28 @@ def shard_lines(number, rank, world_size):
     base, rem = divmod(int(number), int(world_size))
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_plan(G, number, rank, world_size):
+    """(origin_begin, origin_end, line_begin, line_end) of this rank's share of a G x 4 x number root evaluation."""
+    if G >= world_size:
+        o0, o1 = shard_lines(G, rank, world_size)
+        return o0, o1, 0, int(number)
+    l0, l1 = shard_lines(number, rank, world_size)
+    return 0, int(G), l0, l1
+
+
+def embed_partial(part, G, o0, o1):
+    """Partial statistics of origins [o0, o1) -> full [G,4] tensors that are neutral elsewhere (0 for the SUM
+    statistics, INT32_MAX for minmov), ready for allreduce_root_stats."""
+    out = {}
+    for k, neutral in (("logsum", 0), ("count", 0), ("minmov", INT32_MAX)):
+        if part.get(k) is not None:
+            full = torch.full((G, 4), neutral, dtype=part[k].dtype, device=part[k].device)
+            if o1 > o0:
+                full[o0:o1] = part[k]
+            out[k] = full
+    return out
 
 
 def allreduce_root_stats(stats, group=None):
@@ -62,30 +86,43 @@ def min_from_stats(legal, minmov, illegal_value=0):
 
 
 # ---- sharded root evaluations on the GPU --------------------------------------------------------
+def _sharded(run, origins, number, eval_id_base, group):
+    """run(origins, eval_id_base, line_begin, line_end) -> statistics dict of those origins / lines."""
+    rank, ws = world()
+    G = origins.numel()
+    o0, o1, l0, l1 = shard_plan(G, number, rank, ws)
+    if (o0, o1) == (0, G):
+        r = run(origins, eval_id_base, l0, l1)
+    else:
+        r = run(origins, eval_id_base, 0, 0)  # root moves of every origin (legal, rscore); no lines
+        part = run(origins[o0:o1].contiguous(), eval_id_base + o0, l0, l1)  # G >= world size: o1 > o0 on every rank
+        r.update(embed_partial(part, G, o0, o1))
+        if part.get("total_moves") is not None:
+            r["total_moves"] = part["total_moves"]
+    allreduce_root_stats(r, group)
+    if ws > 1 and r.get("total_moves") is not None:
+        dist.all_reduce(r["total_moves"], op=dist.ReduceOp.SUM, group=group)
+    return r
+
+
 def mcts_fixed_sharded(origins, number, seed, eval_id_base=0, group=None):
-    """Fixed-order root search for G origins with the lines sharded over the process group.
+    """Fixed-order root search for G origins sharded over the process group (shard_plan).
     Returns dict(legal, rscore, logsum, count, minmov, mean, min) -- identical on every rank."""
     from . import engine
 
-    rank, ws = world()
-    b, e = shard_lines(number, rank, ws)
-    r = engine.mcts_fixed_lines(origins, number, seed, eval_id_base, b, e, per_line=False, fused=True)
-    allreduce_root_stats(r, group)
+    r = _sharded(lambda o, e, b, l: engine.mcts_fixed_lines(o, number, seed, e, b, l, per_line=False, fused=True),
+                 origins, number, eval_id_base, group)
     r["mean"] = mean_log_from_stats(r["legal"], r["logsum"], r["count"])
     r["min"] = min_from_stats(r["legal"], r["minmov"])
     return r
 
 
 def mcts_nn_sharded(blob, precision, origins, number, seed, eval_id_base=0, group=None):
-    """NN-policy root search (mcts_nn.py:4-43) with the lines sharded over the process group.
-    Early stopping uses each rank's local minimum; the allreduce(MIN) restores the global one."""
+    """NN-policy root search (mcts_nn.py:4-43) sharded over the process group (shard_plan).  With line sharding the
+    early stop uses each rank's local minimum; the allreduce(MIN) restores the global one."""
     from . import engine
 
-    rank, ws = world()
-    b, e = shard_lines(number, rank, ws)
-    r = engine.mcts_nn_lines(blob, precision, origins, number, seed, eval_id_base, b, e)
-    allreduce_root_stats(r, group)
+    r = _sharded(lambda o, e, b, l: engine.mcts_nn_lines(blob, precision, o, number, seed, e, b, l),
+                 origins, number, eval_id_base, group)
     r["min"] = min_from_stats(r["legal"], r["minmov"])
-    if ws > 1:
-        dist.all_reduce(r["total_moves"], op=dist.ReduceOp.SUM, group=group)
     return r

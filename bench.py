@@ -259,7 +259,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout at VERSION/INFO: keep stdout to the one JSON line
+        # NCCL prints its version banner / debug lines on stdout: send them to stderr so stdout is the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("2048nn_b200")
     eng = pkg.engine

@@ -23,14 +23,14 @@ def _free_port():
     return p
 
 
-def _partial(oracle, origins, number, seed, begin, end):
+def _partial(oracle, origins, number, seed, begin, end, eval0=0):
     G = len(origins)
     legal = np.zeros((G, 4), np.uint8)
     logsum = np.zeros((G, 4), np.int64)
     count = np.zeros((G, 4), np.int32)
     minmov = np.full((G, 4), 2**31 - 1, np.int32)
     for g, o in enumerate(origins):
-        lg, rs, sc, mv, _ = oracle.root_lines(int(o), number, seed, g)
+        lg, rs, sc, mv, _ = oracle.root_lines(int(o), number, seed, eval0 + g)
         legal[g] = lg
         for i in range(4):
             if lg[i] and end > begin:
@@ -58,6 +58,15 @@ def _worker(rank, world_size, port, q):
     mean = d.mean_log_from_stats(torch.from_numpy(legal), stats["logsum"], stats["count"])
     mn = d.min_from_stats(torch.from_numpy(legal), stats["minmov"])
     q.put((rank, (b, e), stats["logsum"].numpy().copy(), stats["count"].numpy().copy(), mean.numpy().copy(), mn.numpy().copy()))
+    # origin sharding (G >= world size): the library's own driver with the oracle standing in for the kernels
+    def run(o, eval0, lb, le):
+        lg, ls, ct, mm = _partial(oracle, [int(x) for x in o.numpy().view(np.uint64)], number, seed, lb, le, eval0)
+        return dict(legal=torch.from_numpy(lg), logsum=torch.from_numpy(ls), count=torch.from_numpy(ct), minmov=torch.from_numpy(mm),
+                    total_moves=torch.tensor([int(le - lb) * len(o)]))
+    t_orig = torch.from_numpy(np.array(origins, np.uint64).view(np.int64))
+    plan = d.shard_plan(len(origins), number, rank, world_size)
+    r = d._sharded(run, t_orig, number, 0, None)
+    q.put((10 + rank, plan, r["logsum"].numpy().copy(), r["count"].numpy().copy(), r["minmov"].numpy().copy(), int(r["total_moves"])))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,11 +89,12 @@ def test_allreduce_root_stats_world2(orc):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = [q.get(timeout=120) for _ in range(2)]
+    got = [q.get(timeout=120) for _ in range(4)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    out.sort(key=lambda t: t[0])
+    got.sort(key=lambda t: t[0])
+    out, by_origin = got[:2], got[2:]
     assert out[0][1] == (0, 4) and out[1][1] == (4, 7)
     # every rank holds the same reduced statistics ...
     for k in range(2, 6):
@@ -98,3 +108,17 @@ def test_allreduce_root_stats_world2(orc):
         assert out[0][5][g].tolist() == want_min
         want_mean = orc.mcts_fixed(o, 7, 4242, g)
         assert np.allclose(out[0][4][g], [float(x) for x in want_mean], atol=1e-10, rtol=0)
+    # origin-sharded evaluation: ranks own origins [0,2) and [2,4), all 7 lines, same reduced statistics
+    assert by_origin[0][1] == (0, 2, 0, 7) and by_origin[1][1] == (2, 4, 0, 7)
+    for o in by_origin:
+        assert np.array_equal(o[2], logsum) and np.array_equal(o[3], count) and np.array_equal(o[4], minmov)
+        assert o[5] == 7 * 4
+
+
+def test_shard_plan():
+    d = importlib.import_module("2048nn_b200.dist")
+    assert d.shard_plan(1, 50, 3, 8) == (0, 1) + d.shard_lines(50, 3, 8)      # config 3: one origin -> lines
+    assert d.shard_plan(256, 50, 3, 8) == (96, 128, 0, 50)                    # config 4: whole groups per rank
+    for G, ws in ((8, 8), (9, 4), (2048, 8)):
+        parts = [d.shard_plan(G, 10, r, ws) for r in range(ws)]
+        assert parts[0][0] == 0 and parts[-1][1] == G and all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
