@@ -378,6 +378,10 @@ def main():
         nn_value = nn["moves"] / (nn["ms"] * 1e-3)  # moves are already summed over ranks
         tf = nn_value / world * 5128704.0 / 1e12     # valid-tap FLOP per evaluation, one GPU
         peak_tf = peaks["bf16_tflops_sustained"]
+        nn_traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload (1 GPU, default sizes)
+        npath = os.path.join(ROOT, "profiles", "r01_k4_traffic_nn_block.json")
+        if os.path.exists(npath) and args.nn_origins == 256 and args.nn_lines == 50:
+            nn_traffic = json.load(open(npath))["traffic_bytes_per_launch"]
         line["nn_policy"] = {
             "metric": "playout moves/sec (c64b3 NN-policy, mcts_nn root evaluations)", "value": nn_value, "unit": UNIT,
             "ms_per_step": nn["ms"] / args.steps, "dtype": "fp16 operands / fp32 accumulate (tcgen05)",
@@ -389,7 +393,7 @@ def main():
                              "tflops_valid_taps": nn["fwd_boards_per_s"] * 5128704.0 / 1e12,
                              "frac_of_sustained_peak": nn["fwd_boards_per_s"] * 5128704.0 / 1e12 / peaks["bf16_tflops_sustained"]},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": None,
+                         "traffic": nn_traffic,
                          "note": "5,128,704 valid-tap FLOP per policy evaluation x evals/s on one GPU vs the %s "
                                  "sustained dense bf16/fp16 GEMM peak; the kernel executes 1.2x that (y-padding rows)"
                                  % peak_kind},
