@@ -28,11 +28,11 @@ extern "C" int64_t b2048_train_workspace_bytes(int64_t max_batch) {
 }
 extern "C" int64_t b2048_train_grad_offset(int64_t max_batch) {
     if (max_batch <= 0) return -1;
-    return (int64_t)(reinterpret_cast<char *>(carve(nullptr, max_batch).grad) - reinterpret_cast<char *>(0));
+    return (int64_t)reinterpret_cast<uintptr_t>(carve(nullptr, max_batch).grad);
 }
 extern "C" int64_t b2048_train_logp_offset(int64_t max_batch) {
     if (max_batch <= 0) return -1;
-    return (int64_t)(reinterpret_cast<char *>(carve(nullptr, max_batch).logp) - reinterpret_cast<char *>(0));
+    return (int64_t)reinterpret_cast<uintptr_t>(carve(nullptr, max_batch).logp);
 }
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -43,6 +43,8 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     if (!params || !bn_buffers || !workspace || !boards || !targets || !loss_out)
         return b2048_fail_msg("b2048_train_forward_backward: NULL argument");
     if (B < 2 || B > max_batch) return b2048_fail_msg("b2048_train_forward_backward: need 2 <= B <= max_batch");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(targets) & 15))
+        return b2048_fail_msg("b2048_train_forward_backward: workspace must be 256-byte aligned, targets 16-byte aligned");
     if (int rc = ensure_attrs(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const Workspace w = carve(workspace, max_batch);

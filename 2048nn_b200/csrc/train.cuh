@@ -61,7 +61,7 @@ inline int max_parts(int64_t B) { return (int)((B + 7) / 8 > MAX_PARTS ? (B + 7)
 
 inline Workspace carve(void *base, int64_t B) {
     Workspace w;
-    char *p = reinterpret_cast<char *>(base);
+    const uintptr_t p = reinterpret_cast<uintptr_t>(base);  // base may be NULL: only offsets are wanted then
     size_t off = 0;
     auto take = [&](size_t floats) {
         float *r = reinterpret_cast<float *>(p + off);
