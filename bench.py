@@ -259,9 +259,20 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner / debug lines on stdout: send them to stderr so stdout is the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator comes up: point fd 1 at stderr until
+        # then, so that stdout carries exactly the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     pkg = importlib.import_module("2048nn_b200")
     eng = pkg.engine
     n = args.games
