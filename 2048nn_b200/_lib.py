@@ -52,7 +52,7 @@ _SIGS = {
     "b2048_train_workspace_bytes": (i64, [i64]),
     "b2048_train_grad_offset": (i64, [i64]),
     "b2048_train_logp_offset": (i64, [i64]),
-    "b2048_train_forward_backward": (C.c_int, [P, P, P, P, i64, P, P, i64, C.c_float, P, P]),
+    "b2048_train_forward_backward": (C.c_int, [P, P, P, P, i64, P, P, i64, C.c_float, C.c_int, P, P]),
     "b2048_train_adam": (C.c_int, [P, P, P, P, P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64, P]),
     "b2048_mcts_fixed": (C.c_int, [P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P, P, P]),
 }

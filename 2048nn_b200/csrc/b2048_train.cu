@@ -6,6 +6,7 @@
 #include "../../include/b2048.h"
 #include "capi_internal.h"
 #include "train.cuh"
+#include "train_tc.cuh"
 
 using namespace b2048::train;
 
@@ -18,6 +19,8 @@ static int ensure_attrs(const b2048_ctx *c) {
     CK(cudaFuncSetAttribute(conv3x3_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<16>::BYTES));
     CK(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<64>()));
     CK(cudaFuncSetAttribute(wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<16>()));
+    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
     if (c->device < 64) g_attr_done[c->device] = true;
     return 0;
 }
@@ -39,7 +42,7 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, float *bn_buffers, void *workspace,
                                             int64_t max_batch, const uint64_t *boards, const float *targets, int64_t B,
-                                            float bn_momentum, float *loss_out, void *stream) {
+                                            float bn_momentum, int mixed, float *loss_out, void *stream) {
     if (!params || !bn_buffers || !workspace || !boards || !targets || !loss_out)
         return b2048_fail_msg("b2048_train_forward_backward: NULL argument");
     if (B < 2 || B > max_batch) return b2048_fail_msg("b2048_train_forward_backward: need 2 <= B <= max_batch");
@@ -54,19 +57,37 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     float *run_mean = bn_buffers, *run_var = bn_buffers + 8 * 64;
     const int ew_grid = cdiv(n4, 256);
 
-    pack_weights_kernel<<<cdiv(7 * 9 * 4096, 256), 256, 0, st>>>(params, w.wf, w.wd);
+    const int tiles = cdiv(B, 32);
+    const int g4 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
+    const size_t chunk3 = (size_t)3 * 192 * 64;  // 16-bit elements of one layer's three weight chunks
+    if (mixed) {
+        pack_weights_tc_kernel<<<cdiv((21 + 18) * 192 * 64, 256), 256, 0, st>>>(params, w.wtc_fwd, w.wtc_bwd);
+        onehot_image_kernel<<<cdiv((long)tiles * 512, 256), 256, 0, st>>>((const unsigned long long *)boards, w.img_a, (long)B);
+    } else {
+        pack_weights_kernel<<<cdiv(7 * 9 * 4096, 256), 256, 0, st>>>(params, w.wf, w.wd);
+    }
     onehot_kernel<<<cdiv(rows, 256), 256, 0, st>>>((const unsigned long long *)boards, w.x0, (long)B);
     // ---- forward (network.py:78-87 in training mode: BatchNorm uses batch statistics) -----------------------
     const int conv_grid = cdiv(B, CONV_BOARDS);
     for (int l = 0; l < NL; l++) {
+        const float *res = (l >= 2 && (l & 1) == 0) ? w.a[l - 2] : nullptr;
+        if (mixed) {
+            tc_conv_layer_kernel<false><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
+                w.img_a, reinterpret_cast<const uint8_t *>(w.wtc_fwd + (size_t)l * chunk3), w.z[l], (long)B, l == 0 ? 2 : 4);
+            bn_stats_kernel<<<g4, 256, 0, st>>>((const float4 *)w.z[l], w.part, rows);
+            bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
+                                                   run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
+            bn_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256,
+                                                           (float4 *)w.a[l], w.img_a, n4);
+            continue;
+        }
         if (l == 0)
             conv3x3_kernel<16, true><<<conv_grid, CONV_THREADS, ConvSmem<16>::BYTES, st>>>(w.x0, w.wf, w.z[0], w.part, (long)B);
         else
             conv3x3_kernel<64, true><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.a[l - 1], w.wf + (size_t)l * 36864,
                                                                                            w.z[l], w.part, (long)B);
         bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, conv_grid, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
-                                             run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
-        const float *res = (l >= 2 && (l & 1) == 0) ? w.a[l - 2] : nullptr;
+                                               run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
         bn_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256, (float4 *)w.a[l], n4);
     }
     float *stats7 = w.stats + 7 * 256, *coef7 = w.coef + 7 * 128;
@@ -90,7 +111,6 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     // ---- backward: trunk ----------------------------------------------------------------------------------
     // a[l2] = relu(bn(z[l2]) + a[l2-2]) for l2 = 2,4,6: dy of a block output (dyA) is also the residual gradient of
     // the block input, added when that layer's own dy is formed.
-    const int g4 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
     const int bpc = cdiv(B, WGRAD_SPLITS), splits = cdiv(B, bpc);
     for (int l = NL - 1; l >= 0; l--) {
         const bool even = (l & 1) == 0;
@@ -99,16 +119,24 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         bn_bwd_reduce_kernel<<<g4, 256, 0, st>>>((const float4 *)w.da, (const float4 *)gres, (const float4 *)w.a[l],
                                                  (const float4 *)w.z[l], w.stats + l * 256, (float4 *)dybuf, w.part, rows);
         bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, w.grad + P_G(l), w.grad + P_B(l), w.coef + l * 128, 64);
-        bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                     w.coef + l * 128, (float4 *)w.dz, n4);
+        if (mixed)
+            bn_bwd_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
+                                                               w.coef + l * 128, (float4 *)w.dz, w.img_dz, n4);
+        else
+            bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
+                                                         w.coef + l * 128, (float4 *)w.dz, n4);
         if (l == 0) {
             wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), st>>>(w.x0, w.dz, w.wpart, (long)B, bpc);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(0), 16);
         } else {
             wgrad_kernel<64><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<64>(), st>>>(w.a[l - 1], w.dz, w.wpart, (long)B, bpc);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(l), 64);
-            conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.dz, w.wd + (size_t)l * 36864, w.da,
-                                                                                            nullptr, (long)B);
+            if (mixed)
+                tc_conv_layer_kernel<true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
+                    w.img_dz, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);
+            else
+                conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.dz, w.wd + (size_t)l * 36864, w.da,
+                                                                                                nullptr, (long)B);
         }
     }
     CK(cudaGetLastError());

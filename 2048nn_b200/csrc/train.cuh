@@ -54,6 +54,9 @@ struct Workspace {
     float *hpart;         // [MAX_PARTS][1024] head / loss partials
     float *wf, *wd;       // packed weights [7][9][64 ci][64 co] forward / [7][9][64 co][64 ci] data-gradient
     float *grad;          // [N_PARAMS]
+    // mixed mode (train_tc.cuh): 16-bit operand images of the current conv input / dz, tensor-core weight chunks
+    uint8_t *img_a, *img_dz;  // [ceil(B/32)][65536]
+    uint16_t *wtc_fwd, *wtc_bwd;  // [21][192*64], [18][192*64]
     size_t bytes;
 };
 
@@ -79,6 +82,9 @@ inline Workspace carve(void *base, int64_t B) {
     w.hpart = take((size_t)MAX_PARTS * 1024);
     w.wf = take(7 * 9 * 64 * 64), w.wd = take(7 * 9 * 64 * 64);
     w.grad = take(N_PARAMS);
+    const size_t tiles = (size_t)((B + 31) / 32);
+    w.img_a = reinterpret_cast<uint8_t *>(take(tiles * 16384)), w.img_dz = reinterpret_cast<uint8_t *>(take(tiles * 16384));
+    w.wtc_fwd = reinterpret_cast<uint16_t *>(take(21 * 192 * 32)), w.wtc_bwd = reinterpret_cast<uint16_t *>(take(18 * 192 * 32));
     w.bytes = off;
     return w;
 }

@@ -1,0 +1,243 @@
+// train_tc.cuh -- "mixed" mode of the training step: the 13 forward / data-gradient 3x3 convolutions of a step on
+// the tcgen05 tensor cores (16-bit operands, fp32 accumulation in TMEM); BatchNorm, the head, the weight gradient
+// and Adam stay fp32 (train.cuh).  Same implicit GEMM as the inference kernel (convnet_tc.cuh: column slabs, zero
+// slabs for the y padding, [dx=+1 | 0 | -1] weight chunks, two MMA-issuing warps over accumulator halves), but one
+// layer per launch -- BatchNorm needs the whole batch between two convolutions -- and one tile of 32 boards per CTA:
+//   * the operand image of a tile is produced in global memory already in shared-memory order by the elementwise
+//     kernel before it (bn_apply / bn_bwd_apply / one-hot encoder): 16 slabs x 32 boards x 128 B, SWIZZLE_128B
+//     pre-applied, so the loader is 4 bulk copies (one per board column) + 1 bulk copy of the layer's 3 chunks;
+//   * forward operands are fp16 (activations are O(1) after BatchNorm+ReLU), data-gradient operands bf16 (the
+//     gradient's range, ~1e-8..1e-3, does not fit fp16 without scaling);
+//   * the epilogue writes the raw fp32 accumulators ([board][16 positions][64 channels]) for the fp32 kernels.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "convnet_tc.cuh"
+
+namespace b2048 {
+namespace train {
+
+constexpr int TCL_THREADS = 256;  // warps 0..3 epilogue (TMEM lane quarters), 4 loader, 5/6 MMA issuers, 7 idle
+constexpr int TCL_IMG_BYTES = 16 * tc::SLAB_ROWS * tc::ROW_BYTES;  // 65,536: data slabs of one tile in global memory
+constexpr int TCL_W_BYTES = 3 * tc::CHUNK_BYTES;                   // the layer's three (dy) weight chunks
+constexpr int TCL_SM_W = tc::ACT_BYTES;
+constexpr int TCL_SM_BARS = TCL_SM_W + TCL_W_BYTES;
+constexpr int TCL_SMEM_BYTES = TCL_SM_BARS + 64 + 1024;
+
+// element (board b of the tile, position p, channel ch) of a tile image: byte offset inside the tile
+__device__ __forceinline__ size_t tile_image_offset(int b, int p, int ch) {
+    const int x = p & 3, y = p >> 2;
+    const int row = (x * 4 + y) * tc::SLAB_ROWS + b;             // data slabs only, board-column major
+    const int chunk = (ch >> 3) ^ (b & 7);                       // SWIZZLE_128B: row index % 8 == b % 8 in shared memory
+    return (size_t)row * tc::ROW_BYTES + (size_t)chunk * 16 + (size_t)(ch & 7) * 2;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TCL_THREADS, 1)
+tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restrict__ wchunks, float *__restrict__ out, long B,
+                     int nk) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm_base = tc::smem_u32(sm);
+    const uint32_t bar_full = sm_base + TCL_SM_BARS, bar_acc = bar_full + 8, tmem_slot = bar_full + 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long tile = blockIdx.x;
+    // zero slabs [Z] of the shared image: slabs 0, 5, 10, 15, 20
+    for (int i = tid; i < 5 * tc::SLAB_ROWS * tc::ROW_BYTES / 16; i += TCL_THREADS) {
+        const int z = i / (tc::SLAB_ROWS * tc::ROW_BYTES / 16), r = i % (tc::SLAB_ROWS * tc::ROW_BYTES / 16);
+        reinterpret_cast<uint4 *>(sm + (size_t)z * 5 * tc::SLAB_ROWS * tc::ROW_BYTES)[r] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        tc::mbar_init(bar_full, 1);
+        tc::mbar_init(bar_acc, 2);
+        tc::fence_mbar_init();
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + TCL_SM_BARS + 16);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(bar_full, TCL_IMG_BYTES + TCL_W_BYTES);
+            const uint8_t *src = image + (size_t)tile * TCL_IMG_BYTES;
+#pragma unroll
+            for (int x = 0; x < 4; x++)  // board column x: 4 data slabs (y) behind that column's zero slab
+                tc::bulk_g2s(sm_base + (uint32_t)((5 * x + 1) * tc::SLAB_ROWS * tc::ROW_BYTES), src + (size_t)x * 4 * tc::SLAB_ROWS * tc::ROW_BYTES,
+                             4 * tc::SLAB_ROWS * tc::ROW_BYTES, bar_full);
+            tc::bulk_g2s(sm_base + TCL_SM_W, wchunks, TCL_W_BYTES, bar_full);
+        }
+    } else if (warp == 5 || warp == 6) {
+        const int half = warp - 5;
+        const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
+        tc::mbar_wait(bar_full, 0);
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int dyi = 0; dyi < 3; dyi++)
+            tc::issue_half(sm_base >> 4, (sm_base + TCL_SM_W + dyi * tc::CHUNK_BYTES) >> 4, tmem_base, desc_hi, dyi, nk, half, BF16);
+        tc::umma_commit_elect(bar_acc);
+    } else if (warp < 4) {
+        // thread = (board row y = warp, board = lane): TMEM lane y*32 + board, column block x holds position (y, x)
+        tc::mbar_wait(bar_acc, 0);
+        tc::tc_fence_after();
+        const long board = tile * tc::TILE_BOARDS + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int x = 0; x < 4; x++) {
+            float *o = out + (board * 16 + warp * 4 + x) * 64;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float v[8];
+                tc::tmem_ld8(lane_addr + (uint32_t)(x * 64 + c * 8), reinterpret_cast<uint32_t *>(v));
+                tc::tmem_ld_wait();
+                if (board < B) {
+                    *reinterpret_cast<float4 *>(o + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4 *>(o + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+// ---- operand images -----------------------------------------------------------------------------------------
+// boards -> first-layer image: the one-hot row twice along K (channels [0,16) and [16,32)) against [W_hi | W_lo]
+__global__ void onehot_image_kernel(const unsigned long long *__restrict__ boards, uint8_t *__restrict__ image, long B) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // (board, position)
+    const long tiles = (B + 31) / 32;
+    if (i >= tiles * 32 * 16) return;
+    const long board = i >> 4;
+    const int p = (int)(i & 15), b = (int)(board & 31);
+    const int t = board < B ? (int)((boards[board] >> (4 * p)) & 0xF) : 0;
+    uint8_t *row = image + (size_t)(board >> 5) * TCL_IMG_BYTES + tile_image_offset(b, p, 0) - (size_t)((0 ^ (b & 7)) * 16);
+    const uint32_t one = 0x3C00u << ((t & 1) * 16);  // fp16 1.0 in the right half-word
+    const int wsel = (t & 7) >> 1;
+    const uint4 hot = make_uint4(wsel == 0 ? one : 0u, wsel == 1 ? one : 0u, wsel == 2 ? one : 0u, wsel == 3 ? one : 0u);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const uint4 lo8 = (t < 8) ? hot : zero, hi8 = (t < 8) ? zero : hot;
+    const int sw = b & 7;
+    *reinterpret_cast<uint4 *>(row + ((0 ^ sw) << 4)) = lo8;
+    *reinterpret_cast<uint4 *>(row + ((1 ^ sw) << 4)) = hi8;
+    *reinterpret_cast<uint4 *>(row + ((2 ^ sw) << 4)) = lo8;
+    *reinterpret_cast<uint4 *>(row + ((3 ^ sw) << 4)) = hi8;
+#pragma unroll
+    for (int c = 4; c < 8; c++) *reinterpret_cast<uint4 *>(row + ((c ^ sw) << 4)) = zero;
+}
+
+// four consecutive channels of (board, position) into a tile image, fp16 or bf16
+template <bool BF16>
+__device__ __forceinline__ void store_image4(uint8_t *image, long board, int p, int ch, float4 v) {
+    uint2 w;
+    if (BF16) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
+        w.x = *reinterpret_cast<const uint32_t *>(&a), w.y = *reinterpret_cast<const uint32_t *>(&b2);
+    } else {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b2 = __floats2half2_rn(v.z, v.w);
+        w.x = *reinterpret_cast<const uint32_t *>(&a), w.y = *reinterpret_cast<const uint32_t *>(&b2);
+    }
+    *reinterpret_cast<uint2 *>(image + (size_t)(board >> 5) * TCL_IMG_BYTES + tile_image_offset((int)(board & 31), p, ch)) = w;
+}
+
+// a = relu(z*scale + shift (+ res)) as fp32 and as the next convolution's fp16 operand image
+__global__ void bn_apply_image_kernel(const float4 *__restrict__ z, const float4 *__restrict__ res, const float *__restrict__ stats,
+                                      float4 *__restrict__ a, uint8_t *__restrict__ image, long n4) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c = (int)(i & 15) * 4;
+    const float4 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), sh = *reinterpret_cast<const float4 *>(stats + 192 + c);
+    float4 v = z[i];
+    v.x = fmaf(v.x, sc.x, sh.x), v.y = fmaf(v.y, sc.y, sh.y), v.z = fmaf(v.z, sc.z, sh.z), v.w = fmaf(v.w, sc.w, sh.w);
+    if (res) {
+        const float4 r = res[i];
+        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+    }
+    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    a[i] = v;
+    store_image4<false>(image, i >> 8, (int)((i >> 4) & 15), c, v);
+}
+
+// dz = BatchNorm backward of dy, as fp32 (weight gradient) and as the data-gradient convolution's bf16 operand image
+__global__ void bn_bwd_apply_image_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ z, const float *__restrict__ stats,
+                                          const float *__restrict__ coef, float4 *__restrict__ dz, uint8_t *__restrict__ image, long n4) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c = (int)(i & 15) * 4;
+    const float4 mean = *reinterpret_cast<const float4 *>(stats + c), istd = *reinterpret_cast<const float4 *>(stats + 64 + c),
+                 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), c1 = *reinterpret_cast<const float4 *>(coef + c),
+                 c2 = *reinterpret_cast<const float4 *>(coef + 64 + c);
+    const float4 g = dy[i], zv = z[i];
+    float4 o;
+    o.x = sc.x * (g.x - c1.x - (zv.x - mean.x) * istd.x * c2.x);
+    o.y = sc.y * (g.y - c1.y - (zv.y - mean.y) * istd.y * c2.y);
+    o.z = sc.z * (g.z - c1.z - (zv.z - mean.z) * istd.z * c2.z);
+    o.w = sc.w * (g.w - c1.w - (zv.w - mean.w) * istd.w * c2.w);
+    dz[i] = o;
+    store_image4<true>(image, i >> 8, (int)((i >> 4) & 15), c, o);
+}
+
+// ---- weight chunks ------------------------------------------------------------------------------------------
+// fwd[l][dy] fp16 (21 chunks): rows [dx=+1 | 0 | -1] x 64 co, K = ci; first layer rows are [W_hi(16) | W_lo(16) | 0].
+// bwd[l-1][dy] bf16 (18 chunks, l = 1..6): the data gradient is the same convolution over dz with flipped taps and
+// the channel roles exchanged: rows [dx=+1 | 0 | -1] x 64 ci, K = co, value W[co][ci][2-ky][2-kx].
+__global__ void pack_weights_tc_kernel(const float *__restrict__ params, uint16_t *__restrict__ fwd, uint16_t *__restrict__ bwd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (chunk, row, k)
+    constexpr int PER = tc::CHUNK_ROWS * 64;
+    if (idx >= (21 + 18) * PER) return;
+    const int chunk = idx / PER, row = (idx % PER) >> 6, k = idx & 63;
+    const int blk = row >> 6, n = row & 63, kx = 2 - blk;  // blk 0,1,2 <-> dx = +1, 0, -1 <-> kx = 2, 1, 0
+    const size_t dst = (size_t)chunk * PER + (size_t)row * 64 + (size_t)((((k >> 3) ^ (row & 7)) << 3) | (k & 7));
+    if (chunk < 21) {
+        const int l = chunk / 3, ky = chunk % 3;
+        float v = 0.f;
+        if (l == 0) {
+            if (k < 32) {
+                const float w = params[P_W(0) + ((n * 16 + (k & 15)) * 3 + ky) * 3 + kx];
+                const float hi = __half2float(__float2half_rn(w));
+                v = k < 16 ? hi : w - hi;
+            }
+        } else {
+            v = params[P_W(l) + ((n * 64 + k) * 3 + ky) * 3 + kx];
+        }
+        const __half h = __float2half_rn(v);
+        fwd[dst] = *reinterpret_cast<const uint16_t *>(&h);
+    } else {
+        const int c2 = chunk - 21, l = c2 / 3 + 1, ky = c2 % 3;
+        const float v = params[P_W(l) + ((k * 64 + n) * 3 + (2 - ky)) * 3 + (2 - kx)];  // n = ci, k = co
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        bwd[dst - (size_t)21 * PER] = *reinterpret_cast<const uint16_t *>(&h);
+    }
+}
+
+// per-channel sum / sum of squares of z (BatchNorm batch statistics) for the tensor-core forward, whose epilogue
+// does not see whole channels: 256 threads = 16 channel quads x 16 row lanes, partials [cta][2][64]
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float4 *__restrict__ z, float *__restrict__ part, long rows) {
+    __shared__ float red[2][16][64];
+    const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (long r = (long)blockIdx.x * 16 + rl; r < rows; r += (long)gridDim.x * 16) {
+        const float4 v = z[r * 16 + cq];
+        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x), q.y = fmaf(v.y, v.y, q.y), q.z = fmaf(v.z, v.z, q.z), q.w = fmaf(v.w, v.w, q.w);
+    }
+    *reinterpret_cast<float4 *>(&red[0][rl][cq * 4]) = s;
+    *reinterpret_cast<float4 *>(&red[1][rl][cq * 4]) = q;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; r++) t += red[which][r][c];
+        part[(size_t)blockIdx.x * 128 + which * 64 + c] = t;
+    }
+}
+
+}  // namespace train
+}  // namespace b2048

@@ -246,6 +246,9 @@ int b2048_selfplay_fixed(b2048_ctx *ctx, const uint64_t *starts, int64_t G, uint
  * batch's log-probabilities (float[B*4] at b2048_train_logp_offset).
  * forward_backward: boards u64[B] (the one-hot encoder of game_dataset.py:46-48 is fused), targets f32[B*4];
  *   loss_out device float[1].  Deterministic: batch reductions are summed in a fixed order.
+ *   mixed = 0: every convolution in fp32 on the FFMA2 pipe (the reference's arithmetic; parity mode).
+ *   mixed = 1: the forward and data-gradient convolutions on the tcgen05 tensor cores (fp16 / bf16 operands, fp32
+ *              accumulation), weight gradient, BatchNorm, head and Adam in fp32 -- PyTorch-autocast-like numerics.
  * adam: torch.optim.Adam's update (L2 weight decay added to the gradient, bias correction, eps outside the
  *   square root) for 1-based `step`.  Kept separate so that data-parallel ranks can allreduce the gradient
  *   between the two calls. */
@@ -254,7 +257,7 @@ int64_t b2048_train_grad_offset(int64_t max_batch);
 int64_t b2048_train_logp_offset(int64_t max_batch);
 int b2048_train_forward_backward(b2048_ctx *ctx, const float *params, float *bn_buffers, void *workspace,
                                  int64_t max_batch, const uint64_t *boards, const float *targets, int64_t B,
-                                 float bn_momentum, float *loss_out, void *stream);
+                                 float bn_momentum, int mixed, float *loss_out, void *stream);
 int b2048_train_adam(b2048_ctx *ctx, float *params, const float *grad, float *adam_m, float *adam_v, double lr,
                      double beta1, double beta2, double eps, double weight_decay, int64_t step, void *stream);
 

@@ -9,7 +9,8 @@ rng = np.random.default_rng(0)
 boards = torch.from_numpy(ng["lg_boards"][rng.integers(0, len(ng["lg_boards"]), B)].view(np.int64)).cuda()
 y = torch.softmax(torch.randn(B, 4, device="cuda"), 1)
 torch.manual_seed(0)
-st = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B)
+st = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, use_graph=False,
+                            precision=sys.argv[1] if len(sys.argv) > 1 else "fp32")
 for _ in range(3):
     st.step(boards, y)
 torch.cuda.synchronize()

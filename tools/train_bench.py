@@ -31,11 +31,13 @@ with torch.cuda.stream(s):
     with torch.cuda.graph(g, stream=s):
         L = pkg._lib
         L.check(L.load_library().b2048_train_forward_backward(L.ctx(st.device), L.ptr(st.params), L.ptr(st.bn), L.ptr(st.workspace),
-                st.max_batch, L.ptr(boards), L.ptr(y), B, st.bn_momentum, L.ptr(st.loss), L.stream_ptr(st.device)))
+                st.max_batch, L.ptr(boards), L.ptr(y), B, st.bn_momentum, 0, L.ptr(st.loss), L.stream_ptr(st.device)))
         L.check(L.load_library().b2048_train_adam(L.ctx(st.device), L.ptr(st.params), L.ptr(st.grad), L.ptr(st.m), L.ptr(st.v),
                 st.lr, 0.9, 0.999, 1e-8, 0.0, 100, L.stream_ptr(st.device)))
 us_g = timed(lambda: g.replay())
 print(f"b200 fused step, CUDA graph replay: {us_g:.0f} us/step", flush=True)
+stm = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed")
+print(f"b200 fused step, mixed precision (tcgen05 fwd/dgrad convs), graph: {timed(lambda: stm.step(boards, y)):.0f} us/step", flush=True)
 def fwd(m, x):
     x = m.in_block(x)
     for b in m.blocks: x = m.relu(b(x) + x)
