@@ -21,6 +21,7 @@ static int ensure_attrs(const b2048_ctx *c) {
     CK(cudaFuncSetAttribute(wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(tc_conv_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc_conv_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_SMEM_BYTES));
     if (c->device < 64) g_attr_done[c->device] = true;
     return 0;
 }
@@ -60,9 +61,16 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     const int tiles = cdiv(B, 32);
     const int g4 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
     const size_t chunk3 = (size_t)3 * 192 * 64;  // 16-bit elements of one layer's three weight chunks
+    if (mixed == 2 && (B & 31)) {
+        // the tensor-core weight gradient sums over all 32 rows of a tile: rows of boards past the batch end must be 0
+        const size_t last = (size_t)(tiles - 1) * TCL_IMG_BYTES;
+        CK(cudaMemsetAsync(w.img_dz + last, 0, TCL_IMG_BYTES, st));
+        for (int l = 0; l < NL; l++) CK(cudaMemsetAsync(w.img_abf[l] + last, 0, TCL_IMG_BYTES, st));
+    }
     if (mixed) {
         pack_weights_tc_kernel<<<cdiv((21 + 18) * 192 * 64, 256), 256, 0, st>>>(params, w.wtc_fwd, w.wtc_bwd);
-        onehot_image_kernel<<<cdiv((long)tiles * 512, 256), 256, 0, st>>>((const unsigned long long *)boards, w.img_a, (long)B);
+        onehot_image_kernel<<<cdiv((long)tiles * 512, 256), 256, 0, st>>>((const unsigned long long *)boards, w.img_a, w.img_abf[0],
+                                                                          (long)B);
     } else {
         pack_weights_kernel<<<cdiv(7 * 9 * 4096, 256), 256, 0, st>>>(params, w.wf, w.wd);
     }
@@ -78,7 +86,7 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
             bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
                                                    run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
             bn_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256,
-                                                           (float4 *)w.a[l], w.img_a, n4);
+                                                           (float4 *)w.a[l], w.img_a, l + 1 < NL ? w.img_abf[l + 1] : nullptr, n4);
             continue;
         }
         if (l == 0)
@@ -125,12 +133,17 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         else
             bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
                                                          w.coef + l * 128, (float4 *)w.dz, n4);
-        if (l == 0) {
+        if (mixed == 2) {  // weight gradient on the tensor cores too (bf16 operands)
+            tc_wgrad_kernel<<<tiles, TCL_THREADS, TCW_SMEM_BYTES, st>>>(w.img_abf[l], w.img_dz, w.wpart);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, tiles, w.grad + P_W(l), l == 0 ? 16 : 64);
+        } else if (l == 0) {
             wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), st>>>(w.x0, w.dz, w.wpart, (long)B, bpc);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(0), 16);
         } else {
             wgrad_kernel<64><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<64>(), st>>>(w.a[l - 1], w.dz, w.wpart, (long)B, bpc);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(l), 64);
+        }
+        if (l > 0) {
             if (mixed)
                 tc_conv_layer_kernel<true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
                     w.img_dz, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);

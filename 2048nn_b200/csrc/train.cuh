@@ -50,12 +50,13 @@ struct Workspace {
     float *stats;         // [8][4][64]: mean, invstd, scale, shift
     float *coef;          // [8][2][64]: mean(dy), mean(dy*xhat)
     float *part;          // [max_parts(B)][2][64]
-    float *wpart;         // [WGRAD_SPLITS][9][64][64]
+    float *wpart;         // [max(WGRAD_SPLITS, ceil(B/32))][9][64][64]
     float *hpart;         // [MAX_PARTS][1024] head / loss partials
     float *wf, *wd;       // packed weights [7][9][64 ci][64 co] forward / [7][9][64 co][64 ci] data-gradient
     float *grad;          // [N_PARAMS]
     // mixed mode (train_tc.cuh): 16-bit operand images of the current conv input / dz, tensor-core weight chunks
     uint8_t *img_a, *img_dz;  // [ceil(B/32)][65536]
+    uint8_t *img_abf[NL];     // bf16 copies of every conv layer's input image (weight gradient operands)
     uint16_t *wtc_fwd, *wtc_bwd;  // [21][192*64], [18][192*64]
     size_t bytes;
 };
@@ -78,12 +79,13 @@ inline Workspace carve(void *base, int64_t B) {
     w.h = take((size_t)B * 64), w.dlogits = take((size_t)B * 4), w.logp = take((size_t)B * 4);
     w.stats = take(8 * 4 * 64), w.coef = take(8 * 2 * 64);
     w.part = take((size_t)max_parts(B) * 128);
-    w.wpart = take((size_t)WGRAD_SPLITS * 9 * 64 * 64);
+    w.wpart = take((size_t)((B + 31) / 32 > WGRAD_SPLITS ? (B + 31) / 32 : WGRAD_SPLITS) * 9 * 64 * 64);
     w.hpart = take((size_t)MAX_PARTS * 1024);
     w.wf = take(7 * 9 * 64 * 64), w.wd = take(7 * 9 * 64 * 64);
     w.grad = take(N_PARAMS);
     const size_t tiles = (size_t)((B + 31) / 32);
     w.img_a = reinterpret_cast<uint8_t *>(take(tiles * 16384)), w.img_dz = reinterpret_cast<uint8_t *>(take(tiles * 16384));
+    for (int l = 0; l < NL; l++) w.img_abf[l] = reinterpret_cast<uint8_t *>(take(tiles * 16384));
     w.wtc_fwd = reinterpret_cast<uint16_t *>(take(21 * 192 * 32)), w.wtc_bwd = reinterpret_cast<uint16_t *>(take(18 * 192 * 32));
     w.bytes = off;
     return w;

@@ -108,9 +108,120 @@ tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restric
     if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
+// ---- weight gradient on the tensor cores ----------------------------------------------------------------------
+// dW[tap][ci][co] = sum over rows (board, position) of a[row + tap][ci] * dz[row][co]: a GEMM whose K dimension is the
+// ROW index of both operand images, i.e. both operands are MN-major for tcgen05 (instruction-descriptor bits 15/16):
+// a 128-byte image row is 64 channels along M (resp. N), 8 rows form the SWIZZLE_128B atom along K (SBO = 1024 B).
+// M = 128 stacks two taps: the second 64-channel atom along M sits LBO = 4096 B further = the same window one board row
+// lower, so one MMA accumulates taps (dy, dx) and (dy+1, dx) at once; (dy=+1, dx) is paired with a dummy window whose
+// accumulator rows are ignored.  Per tile of 32 boards: 10 valid (output column, dx) pairs x 8 K-steps x 2 = 160 MMAs
+// (M128 N64 K16), split over two issuing warps by accumulator block; partial dW per tile -> wpart[tile][tap][ci][co].
+constexpr int TCW_SM_B = tc::ACT_BYTES;                 // dz image behind the a image
+constexpr int TCW_SM_BARS = 2 * tc::ACT_BYTES;
+constexpr int TCW_SMEM_BYTES = TCW_SM_BARS + 64 + 1024;
+
+__global__ void __launch_bounds__(TCL_THREADS, 1)
+tc_wgrad_kernel(const uint8_t *__restrict__ img_a, const uint8_t *__restrict__ img_dz, float *__restrict__ wpart) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm_base = tc::smem_u32(sm);
+    const uint32_t bar_full = sm_base + TCW_SM_BARS, bar_acc = bar_full + 8, tmem_slot = bar_full + 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long tile = blockIdx.x;
+    for (int i = tid; i < 5 * tc::SLAB_ROWS * tc::ROW_BYTES / 16; i += TCL_THREADS) {  // zero slabs of the a image
+        const int z = i / (tc::SLAB_ROWS * tc::ROW_BYTES / 16), r = i % (tc::SLAB_ROWS * tc::ROW_BYTES / 16);
+        reinterpret_cast<uint4 *>(sm + (size_t)z * 5 * tc::SLAB_ROWS * tc::ROW_BYTES)[r] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        tc::mbar_init(bar_full, 1);
+        tc::mbar_init(bar_acc, 2);
+        tc::fence_mbar_init();
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + TCW_SM_BARS + 16);
+    constexpr uint32_t SLAB4 = 4 * tc::SLAB_ROWS * tc::ROW_BYTES;  // one board column: 4 data slabs
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(bar_full, 2 * TCL_IMG_BYTES);
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const uint32_t dst = (uint32_t)((5 * x + 1) * tc::SLAB_ROWS * tc::ROW_BYTES);
+                tc::bulk_g2s(sm_base + dst, img_a + (size_t)tile * TCL_IMG_BYTES + (size_t)x * SLAB4, SLAB4, bar_full);
+                tc::bulk_g2s(sm_base + TCW_SM_B + dst, img_dz + (size_t)tile * TCL_IMG_BYTES + (size_t)x * SLAB4, SLAB4, bar_full);
+            }
+        }
+    } else if (warp == 5 || warp == 6) {
+        const int which = warp - 5;  // 0: taps (dy=-1, dy=0) stacked along M; 1: tap dy=+1 (+ ignored dummy rows)
+        // MN-major SWIZZLE_128B descriptors: LBO = 4096 B (next 64-channel atom along M = the window one board row lower),
+        // SBO = 1024 B (next 8 rows along K), version 1, layout SWIZZLE_128B
+        const uint64_t desc_hi = ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
+        const uint32_t idesc = tc::make_idesc(128, 64, true) | (1u << 15) | (1u << 16);
+        tc::mbar_wait(bar_full, 0);
+        tc::tc_fence_after();
+        const uint32_t a_lo = sm_base >> 4, b_lo = (sm_base + TCW_SM_B) >> 4;
+#pragma unroll 1
+        for (int dxi = 0; dxi < 3; dxi++) {
+            const uint32_t d_addr = tmem_base + (uint32_t)((dxi * 2 + which) * 64);
+            bool first = true;
+#pragma unroll 1
+            for (int xs = 0; xs < 4; xs++) {
+                const int xin = xs + dxi - 1;
+                if (xin < 0 || xin > 3) continue;
+                // 16-byte units: a slab-row group is 256 units, a K step of 16 rows is 128 units
+                const uint32_t a0 = a_lo + (uint32_t)((5 * xin + (which ? 2 : 0)) * 256);
+                const uint32_t b0 = b_lo + (uint32_t)((5 * xs + 1) * 256);
+                for (int ks = 0; ks < 8; ks++) {
+                    tc::umma_f16_elect(d_addr, desc_hi | (uint64_t)(a0 + ks * 128), desc_hi | (uint64_t)(b0 + ks * 128), idesc,
+                                       first ? 0u : 1u);
+                    first = false;
+                }
+            }
+        }
+        tc::umma_commit_elect(bar_acc);
+    } else if (warp < 4) {
+        tc::mbar_wait(bar_acc, 0);
+        tc::tc_fence_after();
+        // TMEM lane = row of the stacked M: lanes 0..63 first tap of the block, 64..127 second tap
+        const int m = warp * 32 + lane, ci = m & 63, second = m >> 6;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float *base = wpart + (size_t)tile * 9 * 4096;
+#pragma unroll 1
+        for (int blk = 0; blk < 6; blk++) {
+            const int dxi = blk >> 1, which = blk & 1;
+            const int dyi = which ? 2 : second;  // block 0: dy = -1 / 0 ; block 1: dy = +1 / dummy
+            const bool valid = !(which && second);
+            float *o = base + (size_t)(dyi * 3 + dxi) * 4096 + ci * 64;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float v[8];
+                tc::tmem_ld8(lane_addr + (uint32_t)(blk * 64 + c * 8), reinterpret_cast<uint32_t *>(v));
+                tc::tmem_ld_wait();
+                if (valid) {
+                    *reinterpret_cast<float4 *>(o + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4 *>(o + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ---- operand images -----------------------------------------------------------------------------------------
 // boards -> first-layer image: the one-hot row twice along K (channels [0,16) and [16,32)) against [W_hi | W_lo]
-__global__ void onehot_image_kernel(const unsigned long long *__restrict__ boards, uint8_t *__restrict__ image, long B) {
+// image_bf16 (optional): the plain one-hot row (channels [0,16), bf16) = the first layer's weight-gradient operand
+__global__ void onehot_image_kernel(const unsigned long long *__restrict__ boards, uint8_t *__restrict__ image,
+                                    uint8_t *__restrict__ image_bf16, long B) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // (board, position)
     const long tiles = (B + 31) / 32;
     if (i >= tiles * 32 * 16) return;
@@ -130,6 +241,15 @@ __global__ void onehot_image_kernel(const unsigned long long *__restrict__ board
     *reinterpret_cast<uint4 *>(row + ((3 ^ sw) << 4)) = hi8;
 #pragma unroll
     for (int c = 4; c < 8; c++) *reinterpret_cast<uint4 *>(row + ((c ^ sw) << 4)) = zero;
+    if (image_bf16) {
+        uint8_t *row2 = image_bf16 + (row - image);
+        const uint32_t one2 = 0x3F80u << ((t & 1) * 16);  // bf16 1.0
+        const uint4 hot2 = make_uint4(wsel == 0 ? one2 : 0u, wsel == 1 ? one2 : 0u, wsel == 2 ? one2 : 0u, wsel == 3 ? one2 : 0u);
+        *reinterpret_cast<uint4 *>(row2 + ((0 ^ sw) << 4)) = (t < 8) ? hot2 : zero;
+        *reinterpret_cast<uint4 *>(row2 + ((1 ^ sw) << 4)) = (t < 8) ? zero : hot2;
+#pragma unroll
+        for (int c = 2; c < 8; c++) *reinterpret_cast<uint4 *>(row2 + ((c ^ sw) << 4)) = zero;
+    }
 }
 
 // four consecutive channels of (board, position) into a tile image, fp16 or bf16
@@ -148,7 +268,7 @@ __device__ __forceinline__ void store_image4(uint8_t *image, long board, int p, 
 
 // a = relu(z*scale + shift (+ res)) as fp32 and as the next convolution's fp16 operand image
 __global__ void bn_apply_image_kernel(const float4 *__restrict__ z, const float4 *__restrict__ res, const float *__restrict__ stats,
-                                      float4 *__restrict__ a, uint8_t *__restrict__ image, long n4) {
+                                      float4 *__restrict__ a, uint8_t *__restrict__ image, uint8_t *__restrict__ image_bf16, long n4) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const int c = (int)(i & 15) * 4;
@@ -162,6 +282,7 @@ __global__ void bn_apply_image_kernel(const float4 *__restrict__ z, const float4
     v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
     a[i] = v;
     store_image4<false>(image, i >> 8, (int)((i >> 4) & 15), c, v);
+    if (image_bf16) store_image4<true>(image_bf16, i >> 8, (int)((i >> 4) & 15), c, v);  // kept for the weight gradient
 }
 
 // dz = BatchNorm backward of dy, as fp32 (weight gradient) and as the data-gradient convolution's bf16 operand image

@@ -41,9 +41,11 @@ class TrainStep:
             raise ValueError("model is not a c64b3 ConvNet (231,820 parameters)")
         self.model, self.lr, self.wd, self.betas, self.eps = model, float(lr), float(weight_decay), betas, float(eps)
         self.max_batch, self.bn_momentum = int(max_batch), float(bn_momentum)
-        if precision not in ("fp32", "mixed"):
-            raise ValueError('precision: "fp32" (reference arithmetic) or "mixed" (tensor-core forward / data-gradient convolutions)')
-        self.mixed = int(precision == "mixed")
+        modes = {"fp32": 0, "mixed": 1, "mixed_wgrad": 2}
+        if precision not in modes:
+            raise ValueError('precision: "fp32" (reference arithmetic), "mixed" (tensor-core forward / data-gradient convolutions) '
+                             'or "mixed_wgrad" (weight gradient on the tensor cores too)')
+        self.mixed = modes[precision]
         dev = params[0].device if params[0].device.type == "cuda" else torch.device("cuda")
         self.device = dev
         # flat parameter / buffer vectors; the module's tensors become views of them

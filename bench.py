@@ -215,16 +215,24 @@ def train_step_block(pkg, args, rank, world, barrier):
     boards = torch.randint(0, 2 ** 62, (B * 8,), generator=g, device="cuda", dtype=torch.int64) & 0x7777777777777777
     targets = torch.softmax(torch.randn(B * 8, 4, generator=g, device="cuda"), 1)
     steps = max(10, 4 * args.steps)
-    for k in range(4):
-        st.step(boards[(k % 8) * B:(k % 8 + 1) * B], targets[(k % 8) * B:(k % 8 + 1) * B])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(steps):
-        st.step(boards[(k % 8) * B:(k % 8 + 1) * B], targets[(k % 8) * B:(k % 8 + 1) * B])
-    e1.record()
-    barrier()
-    return {"ms": e0.elapsed_time(e1), "steps": steps, "batch": B, "loss": float(st.loss.item())}
+
+    def run(stepper):
+        for k in range(4):
+            stepper.step(boards[(k % 8) * B:(k % 8 + 1) * B], targets[(k % 8) * B:(k % 8 + 1) * B])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            stepper.step(boards[(k % 8) * B:(k % 8 + 1) * B], targets[(k % 8) * B:(k % 8 + 1) * B])
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    ms = run(st)
+    torch.manual_seed(1234)
+    mixed = pkg.trainer.TrainStep(pkg.network.ConvNet(channels=64, blocks=3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed")
+    ms_mixed = run(mixed)
+    return {"ms": ms, "ms_mixed": ms_mixed, "steps": steps, "batch": B, "loss": float(st.loss.item())}
 
 
 def workload_name(games):
@@ -333,7 +341,7 @@ def main():
     tr = train_step_block(pkg, args, rank, world, barrier) if not args.no_train else None
     clocks = sampler.stop() if rank == 0 else None
 
-    tmax = torch.tensor([ms, e2e_ms] + ([nn["ms"], nn["e2e_ms"]] if nn else [0.0, 0.0]) + [tr["ms"] if tr else 0.0],
+    tmax = torch.tensor([ms, e2e_ms] + ([nn["ms"], nn["e2e_ms"]] if nn else [0.0, 0.0]) + ([tr["ms"], tr["ms_mixed"]] if tr else [0.0, 0.0]),
                         dtype=torch.float64, device="cuda")
     tot = torch.tensor([total_moves, float(e2e_moves)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -344,7 +352,7 @@ def main():
     if nn:
         nn["ms"], nn["e2e_ms"] = tl[2], tl[3]
     if tr:
-        tr["ms"] = tl[4]
+        tr["ms"], tr["ms_mixed"] = tl[4], tl[5]
     total_moves, e2e_moves = tot.tolist()
     if rank != 0:
         if world > 1:
@@ -420,6 +428,10 @@ def main():
                                    "Adam; %s" % (tr["batch"], "gradient allreduce over %d GPUs" % world if world > 1 else "single GPU"),
                        "scaling": "weak"},
             "gpu_launches": 70 * tr["steps"],
+            "mixed_precision": {"us_per_step": tr["ms_mixed"] * 1e3 / tr["steps"],
+                                "value": tr["batch"] * world / (tr["ms_mixed"] * 1e-3 / tr["steps"]), "unit": "samples/s",
+                                "note": "precision=\"mixed\": forward / data-gradient convolutions on tcgen05 (fp16 / bf16 operands, "
+                                        "fp32 accumulate), weight gradient + BatchNorm + Adam fp32"},
             "roofline": {"bound": "fp32_fma", "achieved": flop / (us * 1e-6) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
                          "frac": flop / (us * 1e-6) / 1e12 / fma_peak, "traffic": None,
                          "note": "15.2 MFLOP of in-bounds convolution work per sample vs 148 SM x 128 FMA/clk (FFMA2) at max clock; "

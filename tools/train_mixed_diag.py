@@ -9,7 +9,7 @@ ng = np.load("tests/golden/c64b3_golden.npz")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 ours, ref = T.make_pair(pkg, 1, torch.float64)
 boards, y = T.batch(ng, B, 2)
-st = pkg.trainer.TrainStep(ours, max_batch=2048, precision="mixed", use_graph=False)
+st = pkg.trainer.TrainStep(ours, max_batch=2048, precision=sys.argv[2] if len(sys.argv) > 2 else "mixed", use_graph=False)
 loss = st.forward_backward(boards, y)
 torch.cuda.synchronize()
 lp = T.torch_forward(ref, T.onehot(boards).double())
