@@ -28,8 +28,9 @@ class TrainStep:
 
     step(boards, targets) == trainer.py:56-62 (zero_grad, forward in train mode, KLDivLoss(batchmean), backward,
     Adam step) for one batch: boards int64 (uint64 bit patterns) [B], targets float32 [B,4].  Returns the loss as a
-    0-d device tensor (no host sync).  precision="mixed" runs the forward / data-gradient convolutions on the tensor
-    cores (fp16 / bf16 operands, fp32 accumulation; everything else fp32) -- about twice as fast, autocast-like numerics."""
+    0-d device tensor (no host sync).  precision="mixed" runs the forward / data-gradient / weight-gradient convolutions
+    on the tensor cores (fp16 / bf16 operands, fp32 accumulation; BatchNorm, head, Adam and the master weights fp32) --
+    about twice as fast, autocast-like numerics."""
 
     def __init__(self, model, lr=0.1, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_batch=2048, bn_momentum=0.1,
                  use_graph=True, precision="fp32"):
@@ -41,10 +42,10 @@ class TrainStep:
             raise ValueError("model is not a c64b3 ConvNet (231,820 parameters)")
         self.model, self.lr, self.wd, self.betas, self.eps = model, float(lr), float(weight_decay), betas, float(eps)
         self.max_batch, self.bn_momentum = int(max_batch), float(bn_momentum)
-        modes = {"fp32": 0, "mixed": 1, "mixed_wgrad": 2}
+        modes = {"fp32": 0, "mixed_fp32_wgrad": 1, "mixed": 2}
         if precision not in modes:
-            raise ValueError('precision: "fp32" (reference arithmetic), "mixed" (tensor-core forward / data-gradient convolutions) '
-                             'or "mixed_wgrad" (weight gradient on the tensor cores too)')
+            raise ValueError('precision: "fp32" (reference arithmetic), "mixed" (all 3x3 convolutions -- forward, data gradient, '
+                             'weight gradient -- on the tensor cores) or "mixed_fp32_wgrad" (weight gradient kept in fp32)')
         self.mixed = modes[precision]
         dev = params[0].device if params[0].device.type == "cuda" else torch.device("cuda")
         self.device = dev

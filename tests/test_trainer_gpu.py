@@ -219,15 +219,17 @@ def test_trainer_main_loop(pkg, ng, tmp_path, capsys):
     assert "Train mLoss" in capsys.readouterr().out
 
 
-@pytest.mark.parametrize("B", [250, 2048])
-def test_mixed_precision_step_tracks_fp64(pkg, ng, B):
-    # precision="mixed": forward / data-gradient convolutions on the tensor cores (fp16 / bf16 operands, fp32 accumulate).
+@pytest.mark.parametrize("B,mode", [(250, "mixed"), (2048, "mixed"), (250, "mixed_fp32_wgrad"), (32, "mixed"), (33, "mixed")])
+def test_mixed_precision_step_tracks_fp64(pkg, ng, B, mode):
+    # precision="mixed": forward / data-gradient / weight-gradient convolutions on the tensor cores (fp16 / bf16 operands,
+    # fp32 accumulate; the weight gradient uses MN-major operands and sums over whole 32-board tiles -> ragged B checked).
     # Bar = autocast-like agreement with fp64 autograd: loss 1e-3, log-probs 5e-3, every gradient tensor within 10 % in
     # L2 and cosine >= 0.995 (measured: loss 1.4e-5, log-probs 5e-4, 1.5-4 %, >= 0.9991; most of it ReLU branch flips
     # of activations that fp16 moves across 0)
     ours, ref = make_pair(pkg, 1, torch.float64)
     boards, y = batch(ng, B, 2)
-    stepper = pkg.trainer.TrainStep(ours, max_batch=2048, precision="mixed")
+    stepper = pkg.trainer.TrainStep(ours, max_batch=2048, precision=mode)
+    stepper.workspace.fill_(0xFF)  # stale / NaN bit patterns everywhere: rows past the batch end must not leak in
     loss = float(stepper.forward_backward(boards, y).item())
     ref_logp = torch_forward(ref, onehot(boards).double())
     ref_loss = nn.KLDivLoss(reduction='batchmean')(ref_logp, y.double())
@@ -241,7 +243,7 @@ def test_mixed_precision_step_tracks_fp64(pkg, ng, B):
         off += n
         rel = float((mine - p.grad).norm() / p.grad.norm())
         cos = float((mine * p.grad).sum() / (mine.norm() * p.grad.norm()))
-        assert rel < 0.1 and cos > 0.995, (name, rel, cos)
+        assert rel < (0.1 if B >= 250 else 0.2) and cos > (0.995 if B >= 250 else 0.98), (name, rel, cos)
 
 
 def test_mixed_precision_training_converges_like_fp32(pkg, ng):

@@ -36,9 +36,9 @@ with torch.cuda.stream(s):
                 st.lr, 0.9, 0.999, 1e-8, 0.0, 100, L.stream_ptr(st.device)))
 us_g = timed(lambda: g.replay())
 print(f"b200 fused step, CUDA graph replay: {us_g:.0f} us/step", flush=True)
-stm = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed")
+stm = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed_fp32_wgrad")
 print(f"b200 fused step, mixed precision (tcgen05 fwd/dgrad convs), graph: {timed(lambda: stm.step(boards, y)):.0f} us/step", flush=True)
-stw = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed_wgrad")
+stw = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=B, precision="mixed")
 print(f"b200 fused step, mixed + tensor-core weight gradient, graph: {timed(lambda: stw.step(boards, y)):.0f} us/step", flush=True)
 def fwd(m, x):
     x = m.in_block(x)
