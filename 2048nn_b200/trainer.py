@@ -183,7 +183,8 @@ def main(args):
         print('Loaded ' + args.pretrained)
         logname = 'pre_' + logname
     m.to(device)
-    stepper = TrainStep(m, lr=args.lr, weight_decay=args.decay, max_batch=args.batch_size)
+    stepper = TrainStep(m, lr=args.lr, weight_decay=args.decay, max_batch=args.batch_size,
+                        precision=getattr(args, "precision", "fp32"))
     t_loss, min_move = [], []
     best, timer = 0.0, 0
     stop = args.epochs if args.patience == 0 else args.patience
@@ -235,6 +236,8 @@ def parser():
     p.add_argument('--name', type=str, default='', help='Additional prepend output name')
     p.add_argument('--seed', type=int, default=0)
     p.add_argument('--pretrained', type=str, default='', help='Path to network to continue training')
+    p.add_argument('--precision', type=str, default='fp32', choices=['fp32', 'mixed'],
+                   help='fp32 = the reference arithmetic; mixed = convolutions on the tensor cores (not in the reference)')
     return p
 
 
