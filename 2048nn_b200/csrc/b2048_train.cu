@@ -11,9 +11,13 @@
 using namespace b2048::train;
 
 static bool g_attr_done[64] = {};
+// mixed mode: the tensor-core weight gradient of layer l overlaps the data gradient / BatchNorm backward of the layers
+// below it on a side stream (fork/join with events; legal under stream capture, so the CUDA graph keeps the branches)
+static cudaStream_t g_side[64] = {};
+static cudaEvent_t g_fork[64][NL] = {}, g_done[64][NL] = {};
 
 static int ensure_attrs(const b2048_ctx *c) {
-    if (c->device < 64 && g_attr_done[c->device]) return 0;
+    if (c->device >= 0 && c->device < 64 && g_attr_done[c->device]) return 0;
     CK(cudaFuncSetAttribute(conv3x3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<64>::BYTES));
     CK(cudaFuncSetAttribute(conv3x3_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<64>::BYTES));
     CK(cudaFuncSetAttribute(conv3x3_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<16>::BYTES));
@@ -22,7 +26,13 @@ static int ensure_attrs(const b2048_ctx *c) {
     CK(cudaFuncSetAttribute(tc_conv_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc_conv_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_SMEM_BYTES));
-    if (c->device < 64) g_attr_done[c->device] = true;
+    if (c->device >= 64) return b2048_fail_msg("b2048 training: device index above 63");
+    CK(cudaStreamCreateWithFlags(&g_side[c->device], cudaStreamNonBlocking));
+    for (int l = 0; l < NL; l++) {
+        CK(cudaEventCreateWithFlags(&g_fork[c->device][l], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g_done[c->device][l], cudaEventDisableTiming));
+    }
+    g_attr_done[c->device] = true;
     return 0;
 }
 
@@ -65,6 +75,7 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         // the tensor-core weight gradient sums over all 32 rows of a tile: rows of boards past the batch end must be 0
         const size_t last = (size_t)(tiles - 1) * TCL_IMG_BYTES;
         CK(cudaMemsetAsync(w.img_dz + last, 0, TCL_IMG_BYTES, st));
+        CK(cudaMemsetAsync(w.img_dz2 + last, 0, TCL_IMG_BYTES, st));
         for (int l = 0; l < NL; l++) CK(cudaMemsetAsync(w.img_abf[l] + last, 0, TCL_IMG_BYTES, st));
     }
     if (mixed) {
@@ -127,15 +138,24 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         bn_bwd_reduce_kernel<<<g4, 256, 0, st>>>((const float4 *)w.da, (const float4 *)gres, (const float4 *)w.a[l],
                                                  (const float4 *)w.z[l], w.stats + l * 256, (float4 *)dybuf, w.part, rows);
         bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, w.grad + P_G(l), w.grad + P_B(l), w.coef + l * 128, 64);
-        if (mixed)
+        uint8_t *dz_img = (mixed == 2 && (l & 1)) ? w.img_dz2 : w.img_dz;
+        if (mixed) {
+            // the weight gradient of layer l+2 read this dz buffer on the side stream: it must be done before the rewrite
+            if (mixed == 2 && l + 2 < NL) CK(cudaStreamWaitEvent(st, g_done[c->device][l + 2], 0));
             bn_bwd_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                               w.coef + l * 128, (float4 *)w.dz, w.img_dz, n4);
-        else
+                                                               w.coef + l * 128, (float4 *)w.dz, dz_img, n4);
+        } else {
             bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
                                                          w.coef + l * 128, (float4 *)w.dz, n4);
-        if (mixed == 2) {  // weight gradient on the tensor cores too (bf16 operands)
-            tc_wgrad_kernel<<<tiles, TCL_THREADS, TCW_SMEM_BYTES, st>>>(w.img_abf[l], w.img_dz, w.wpart);
-            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, tiles, w.grad + P_W(l), l == 0 ? 16 : 64);
+        }
+        if (mixed == 2) {  // weight gradient on the tensor cores (bf16 operands), off the critical path
+            cudaStream_t side = g_side[c->device];
+            CK(cudaEventRecord(g_fork[c->device][l], st));
+            CK(cudaStreamWaitEvent(side, g_fork[c->device][l], 0));
+            tc_wgrad_kernel<<<tiles, TCL_THREADS, TCW_SMEM_BYTES, side>>>(w.img_abf[l], dz_img, w.wpart);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, side>>>(w.wpart, tiles, w.grad + P_W(l), l == 0 ? 16 : 64);
+            CK(cudaEventRecord(g_done[c->device][l], side));
+            if (l == 0) CK(cudaStreamWaitEvent(st, g_done[c->device][0], 0));  // join: the side stream is in order
         } else if (l == 0) {
             wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), st>>>(w.x0, w.dz, w.wpart, (long)B, bpc);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(0), 16);
@@ -146,7 +166,7 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         if (l > 0) {
             if (mixed)
                 tc_conv_layer_kernel<true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
-                    w.img_dz, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);
+                    dz_img, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);
             else
                 conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.dz, w.wd + (size_t)l * 36864, w.da,
                                                                                                 nullptr, (long)B);

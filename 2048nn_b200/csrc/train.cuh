@@ -55,7 +55,7 @@ struct Workspace {
     float *wf, *wd;       // packed weights [7][9][64 ci][64 co] forward / [7][9][64 co][64 ci] data-gradient
     float *grad;          // [N_PARAMS]
     // mixed mode (train_tc.cuh): 16-bit operand images of the current conv input / dz, tensor-core weight chunks
-    uint8_t *img_a, *img_dz;  // [ceil(B/32)][65536]
+    uint8_t *img_a, *img_dz, *img_dz2;  // [ceil(B/32)][65536]; dz double-buffered (weight gradient runs on a side stream)
     uint8_t *img_abf[NL];     // bf16 copies of every conv layer's input image (weight gradient operands)
     uint16_t *wtc_fwd, *wtc_bwd;  // [21][192*64], [18][192*64]
     size_t bytes;
@@ -85,6 +85,7 @@ inline Workspace carve(void *base, int64_t B) {
     w.grad = take(N_PARAMS);
     const size_t tiles = (size_t)((B + 31) / 32);
     w.img_a = reinterpret_cast<uint8_t *>(take(tiles * 16384)), w.img_dz = reinterpret_cast<uint8_t *>(take(tiles * 16384));
+    w.img_dz2 = reinterpret_cast<uint8_t *>(take(tiles * 16384));
     for (int l = 0; l < NL; l++) w.img_abf[l] = reinterpret_cast<uint8_t *>(take(tiles * 16384));
     w.wtc_fwd = reinterpret_cast<uint16_t *>(take(21 * 192 * 32)), w.wtc_bwd = reinterpret_cast<uint16_t *>(take(18 * 192 * 32));
     w.bytes = off;
