@@ -236,17 +236,25 @@ static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     unsigned slot = (c->next_counter++) % N_COUNTERS;
     p.counter = c->counters + slot;
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
-    int grid = grid_for(p.n, 1024, c->num_sms);
+    // one CTA per SM; fewer games than 1024 x #SMs are spread over all SMs with narrower CTAs instead of filling a few
+    // SMs (the kernels take their stride from blockDim): 64 K games = 148 x 448 threads rather than 64 x 1024
+    int grid = c->num_sms, block = 1024;
+    if (p.n < (long)c->num_sms * 1024) {
+        long per_sm = (p.n + c->num_sms - 1) / c->num_sms;
+        block = (int)(((per_sm + 31) / 32) * 32);
+        if (block < 64) block = 64;
+        grid = (int)((p.n + block - 1) / block);
+    }
     bool ludr = p.order[0] == 0 && p.order[1] == 1 && p.order[2] == 3 && p.order[3] == 2;
     if (c->k2_variant == 1) {
         if (ludr)
-            playout_fixed_kernel2<true><<<grid, 1024, K2V2_SMEM_BYTES, st>>>(p);
+            playout_fixed_kernel2<true><<<grid, block, K2V2_SMEM_BYTES, st>>>(p);
         else
-            playout_fixed_kernel2<false><<<grid, 1024, K2V2_SMEM_BYTES, st>>>(p);
+            playout_fixed_kernel2<false><<<grid, block, K2V2_SMEM_BYTES, st>>>(p);
     } else if (ludr) {
-        playout_fixed_kernel<true><<<grid, 1024, 131072, st>>>(p);
+        playout_fixed_kernel<true><<<grid, block, 131072, st>>>(p);
     } else {
-        playout_fixed_kernel<false><<<grid, 1024, 131072, st>>>(p);
+        playout_fixed_kernel<false><<<grid, block, 131072, st>>>(p);
     }
     CK(cudaGetLastError());
     return 0;
