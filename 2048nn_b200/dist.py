@@ -3,8 +3,9 @@
 Playouts are independent, so a root evaluation shards over the ranks with the same (seed, eval_id) keyed
 streams -- by ORIGINS when there are at least as many origins as ranks (config 4: every rank evaluates whole
 (origin, root move) groups, so the early stop of the min-move search prunes exactly as on one GPU), else by LINES
-(config 3: rank r plays lines [begin_r, end_r) of every group) -- and the ranks combine their partial statistics
-with ONE small allreduce:
+(rank r plays lines [begin_r, end_r) of every group; a config-3-sized evaluation that fits one GPU's game slots is
+replicated instead, see shard_plan) -- and the ranks combine their partial statistics with ONE small allreduce
+(SURVEY.md 8e):
 
     mean-log (mcts.py:4-34)      logsum i64[G,4] fixed-point + count i32[G,4]   SUM
     min-move (mcts.py:73-103,
@@ -35,11 +36,19 @@ def shard_lines(number, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+REPLICATE_BELOW_LINES = 148 * 32  # one 32-board tile-set per SM: a root evaluation this small is latency-bound
+
+
 def shard_plan(G, number, rank, world_size):
-    """(origin_begin, origin_end, line_begin, line_end) of this rank's share of a G x 4 x number root evaluation."""
+    """(origin_begin, origin_end, line_begin, line_end) of this rank's share of a G x 4 x number root evaluation.
+    The whole range on every rank means "replicated": fewer origins than ranks and so few lines that one GPU runs
+    them all concurrently -- the call is bound by the longest line, splitting it only weakens the early stop and
+    adds an exchange, so every rank computes the (identical, deterministic) result itself and nothing is reduced."""
     if G >= world_size:
         o0, o1 = shard_lines(G, rank, world_size)
         return o0, o1, 0, int(number)
+    if world_size > 1 and 4 * int(G) * int(number) <= REPLICATE_BELOW_LINES:
+        return 0, int(G), 0, int(number)
     l0, l1 = shard_lines(number, rank, world_size)
     return 0, int(G), l0, l1
 
@@ -91,6 +100,8 @@ def _sharded(run, origins, number, eval_id_base, group):
     rank, ws = world()
     G = origins.numel()
     o0, o1, l0, l1 = shard_plan(G, number, rank, ws)
+    if ws > 1 and (o0, o1, l0, l1) == (0, G, 0, int(number)):
+        return run(origins, eval_id_base, 0, int(number))  # replicated: identical on every rank, no exchange
     if (o0, o1) == (0, G):
         r = run(origins, eval_id_base, l0, l1)
     else:

@@ -117,7 +117,8 @@ def test_allreduce_root_stats_world2(orc):
 
 def test_shard_plan():
     d = importlib.import_module("2048nn_b200.dist")
-    assert d.shard_plan(1, 50, 3, 8) == (0, 1) + d.shard_lines(50, 3, 8)      # config 3: one origin -> lines
+    assert d.shard_plan(1, 50, 3, 8) == (0, 1, 0, 50)                         # config 3: 200 lines -> replicated, no exchange
+    assert d.shard_plan(2, 2000, 3, 8) == (0, 2) + d.shard_lines(2000, 3, 8)  # few origins, many lines -> lines
     assert d.shard_plan(256, 50, 3, 8) == (96, 128, 0, 50)                    # config 4: whole groups per rank
     for G, ws in ((8, 8), (9, 4), (2048, 8)):
         parts = [d.shard_plan(G, 10, r, ws) for r in range(ws)]
