@@ -14,17 +14,17 @@ m.load_state_dict({k[len("sd_shipped/"):]: torch.from_numpy(np.array(ng[k])) for
 m.cuda().eval()
 blob = m.blob("fp16")
 ok = True
-for G in (1, world, 2 * world + 1):  # line sharding, one origin per rank, ragged origin blocks
+for G, number in ((1, 12), (1, 1300), (world, 12), (2 * world + 1, 12)):  # replicated, line-sharded, origin-sharded (even / ragged)
     origins = eng.init_boards(G, 31, 0)
-    r = d.mcts_nn_sharded(blob, "fp16", origins, 12, 5, 100)
-    one = eng.mcts_nn_lines(blob, "fp16", origins, 12, 5, 100)
+    r = d.mcts_nn_sharded(blob, "fp16", origins, number, 5, 100)
+    one = eng.mcts_nn_lines(blob, "fp16", origins, number, 5, 100)
     same = torch.equal(r["min"], d.min_from_stats(one["legal"], one["minmov"]))
-    f = d.mcts_fixed_sharded(origins, 10, 5, 7)
-    f1 = eng.mcts_fixed_lines(origins, 10, 5, 7, per_line=False, fused=True)
+    f = d.mcts_fixed_sharded(origins, number, 5, 7)
+    f1 = eng.mcts_fixed_lines(origins, number, 5, 7, per_line=False, fused=True)
     same_f = torch.equal(f["logsum"], f1["logsum"]) and torch.equal(f["count"], f1["count"]) and torch.equal(f["minmov"], f1["minmov"])
     ok &= same and same_f
     if rank == 0:
-        print(f"G={G}: plan {d.shard_plan(G, 12, rank, world)} mcts_nn {'ok' if same else 'MISMATCH'}, mcts_fixed {'ok' if same_f else 'MISMATCH'}", flush=True)
+        print(f"G={G} number={number}: plan {d.shard_plan(G, number, rank, world)} mcts_nn {'ok' if same else 'MISMATCH'}, mcts_fixed {'ok' if same_f else 'MISMATCH'}", flush=True)
 recs, mv = pkg.selfplay.selfplay_batch(2 * world + 1, 6, None, 2, seed=9)
 single = eng.selfplay_fixed_games(2 * world + 1, 6, 9, times=2, mode=2)
 steps = single["steps"].cpu().numpy()
