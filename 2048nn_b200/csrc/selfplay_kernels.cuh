@@ -36,29 +36,39 @@ struct SelfplayParams {
     int *err_flag;
 };
 
-// one fixed-order (L,U,D,R) line from `b` to its end (board.py:192-225 semantics on injected spawns)
+// one fixed-order (L,U,D,R) line from `b` to its end (board.py:192-225 semantics on injected spawns).  Legality first
+// (8 byte lookups: rows of the board and of its transpose), then ONE table slide in the chosen direction -- the same
+// scheme as K2 variant 1, with the tables read through L1 instead of shared memory.
+template <bool NEED_SCORE>
 __device__ __forceinline__ void play_line(const Tables &tb, u64 b, u64 key, u32 &score, u32 &count, int *err_flag) {
     score = 0, count = 0;
+    const uint8_t *__restrict__ L = tb.legal;
+    const uint16_t *__restrict__ T = tb.fin_fwd;
     for (;;) {
-        u32 s;
-        u64 f = move_exact(b, 0, tb, s);
-        if (f == b) {
-            f = move_exact(b, 1, tb, s);
-            if (f == b) {
-                f = move_exact(b, 3, tb, s);
-                if (f == b) {
-                    f = move_exact(b, 2, tb, s);
-                    if (f == b) return;
-                }
-            }
-        }
-        if (countzero(f) == 0) {
+        const u64 bt = transpose(b);
+        const u32 lo = lo32(b), hi = hi32(b), tlo = lo32(bt), thi = hi32(bt);
+        const u32 hm = __ldg(L + (lo & 0xFFFFu)) | __ldg(L + (lo >> 16)) | __ldg(L + (hi & 0xFFFFu)) | __ldg(L + (hi >> 16));
+        const u32 vm = __ldg(L + (tlo & 0xFFFFu)) | __ldg(L + (tlo >> 16)) | __ldg(L + (thi & 0xFFFFu)) | __ldg(L + (thi >> 16));
+        if (!(hm | vm)) return;
+        const u32 d = (hm & 1u) ? 0u : (vm & 1u) ? 1u : (vm & 2u) ? 3u : 2u;  // first legal of L, U, D, R
+        u64 x = (d & 1u) ? bt : b;
+        const bool rev = (d & 2u) != 0;
+        const u64 xm = mirror(x);
+        x = rev ? xm : x;
+        const u32 xl = lo32(x), xh = hi32(x);
+        const u32 r0 = xl & 0xFFFFu, r1 = xl >> 16, r2 = xh & 0xFFFFu, r3 = xh >> 16;
+        u64 y = pack64(__ldg(T + r0) | ((u32)__ldg(T + r1) << 16), __ldg(T + r2) | ((u32)__ldg(T + r3) << 16));
+        if (NEED_SCORE) score += __ldg(tb.score + r0) + __ldg(tb.score + r1) + __ldg(tb.score + r2) + __ldg(tb.score + r3);
+        const u64 ym = mirror(y);
+        y = rev ? ym : y;
+        const u64 yt = transpose(y);
+        y = (d & 1u) ? yt : y;
+        if (countzero(y) == 0) {
             *err_flag = 1;
             return;
         }
         u32 four;
-        b = spawn_tile(f, rng_draw(key, B2048_INIT_DRAWS + 1 + count), four);
-        score += s;
+        b = spawn_tile(y, rng_draw(key, B2048_INIT_DRAWS + 1 + count), four);
         count++;
     }
 }
@@ -108,7 +118,9 @@ __global__ void selfplay_fixed_kernel(const SelfplayParams p) {
             const u64 eval_id = ((u64)step * (u64)p.times + (u64)t + 1ULL) * p.g_total + gid_main;
             const u64 key = rng_key(p.seed, (eval_id * 4ULL + (u64)i) * (u64)p.number + (u64)j);
             u32 four, sc, cnt;
-            play_line(p.tb, spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four), key, sc, cnt, p.err_flag);
+            const u64 first = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);
+            if (p.mode == B2048_MODE_MEANLOG) play_line<true>(p.tb, first, key, sc, cnt, p.err_flag);
+            else play_line<false>(p.tb, first, key, sc, cnt, p.err_flag);
             moves_done += cnt;
             if (p.mode == B2048_MODE_MEANLOG) {
                 const double lg = log10((double)sc + (double)s_rscore[i] + 1.0);  // mcts.py:31
