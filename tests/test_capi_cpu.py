@@ -58,3 +58,29 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle|oracle/|libb2048_oracle", txt, re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: the header must compile as C99 with no C++ / torch types
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b2048.h"\nint main(void) { return b2048_abi_version() == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_new_entry_points_fail_loudly_without_gpu(built, pkg):
+    # trainer, population evaluation, analysis and device-resident games: no CPU fallback either
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    m = pkg.network.ConvNet(64, 3)
+    with pytest.raises(pkg.B2048Error):
+        pkg.trainer.TrainStep(m)
+    with pytest.raises(pkg.B2048Error):
+        pkg.mcts.play_mcts_fixed(number=2, seed=1)
+    with pytest.raises(pkg.B2048Error):
+        pkg.analysis.fixed_distribution(8, seed=1)
+    with pytest.raises(pkg.B2048Error):
+        pkg.evolve.eval_population([m], number=2, seed=1)
