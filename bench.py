@@ -404,7 +404,8 @@ def main():
         line["nn_policy"] = {
             "metric": "playout moves/sec (c64b3 NN-policy, mcts_nn root evaluations)", "value": nn_value, "unit": UNIT,
             "ms_per_step": nn["ms"] / args.steps, "dtype": "fp16 operands / fp32 accumulate (tcgen05)",
-            "config": {"workload": nn["workload"], "weights": nn["weights"], "scaling": "weak"},
+            "config": {"workload": nn["workload"], "weights": nn["weights"], "scaling": "weak",
+                       "l2": "compute-bound kernel: per-step inputs are 8 B per origin, the 0.5 MB weight image is L2-resident by design"},
             "e2e": {"value": nn["e2e_moves"] / (nn["e2e_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": nn["h2d"], "d2h_bytes_per_step": nn["d2h"]},
             "gpu_launches": 2 * args.steps,
