@@ -95,6 +95,10 @@ class TrainStep:
             raise ValueError("boards: int64 [B], targets: float32 [B,4]")
         if B > self.max_batch:
             raise ValueError("batch larger than max_batch")
+        first = next(self.model.parameters())
+        if first.data_ptr() != self.params.data_ptr():
+            raise RuntimeError("the model's parameters no longer alias the trainer's flat buffer (model.to()/.cpu() after "
+                               "TrainStep was built?): build a new TrainStep for the moved model")
         if not self.use_graph:
             self._enqueue(boards, targets, B)
         else:
