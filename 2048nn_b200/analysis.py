@@ -66,16 +66,18 @@ def policy_distribution(model, n=5000, seed=None, precision=None, chunk=1 << 20,
     return _collect(play, n, chunk, rows)
 
 
-def mcts_distribution(number, times, mode=0, seed=None):
-    """distribution.py:17-36: `times` main games of play_mcts_fixed(number, mode) -> rows [max tile, score, moves]."""
-    from .mcts import play_mcts_fixed
-    from .board import get_tiles
+def mcts_distribution(number, times, mode=0, seed=None, max_steps=8192):
+    """distribution.py:17-36: `times` main games of play_mcts_fixed(number, mode) -> rows [max tile, score, moves].
+    All games run concurrently in one launch of the device-resident main-game kernel (game g = stream (seed, g))."""
     s = _session_seed(seed)
-    out = []
-    for g in range(times):
-        board, score, count = play_mcts_fixed(number=number, mode=mode, seed=(s + g) & (2 ** 64 - 1))
-        out.append([max(get_tiles(board)), score, count])
-    return np.array(out)
+    while True:
+        r = engine.selfplay_fixed_games(int(times), int(number), s, times=1, mode=int(mode), max_steps=max_steps, record=False)
+        _raise_if_flag()
+        if not bool((r["status"] != 0).any().item()):
+            break
+        max_steps *= 8
+    _, mt = engine.game_summary(r["final"], r["score"].to(torch.int32), r["steps"], want_maxtile=True)
+    return torch.stack([mt.to(torch.int64), r["score"], r["steps"].to(torch.int64)], 1).cpu().numpy()
 
 
 def weibull_fit(x, loc, scale):

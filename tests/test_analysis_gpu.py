@@ -54,3 +54,15 @@ def test_shipped_policy_pins(pkg, ng):
     b = pkg.analysis.policy_distribution(m, 3000, seed=2, rows=True)["rows"][:, 1]
     ks, _ = pkg.analysis.compare(a, b)
     assert ks.pvalue > 1e-3  # two seeds of one model: same distribution
+
+
+def test_mcts_distribution_rows(pkg):
+    # distribution.py:17-36 shape: one row [max tile exponent, score, moves] per play_mcts_fixed game
+    rows = pkg.analysis.mcts_distribution(5, 6, mode=2, seed=21)
+    assert rows.shape == (6, 3) and (rows[:, 2] > 50).all() and (rows[:, 0] >= 6).all()
+    assert np.array_equal(rows, pkg.analysis.mcts_distribution(5, 6, mode=2, seed=21))  # reproducible
+    one = pkg.mcts.play_mcts_fixed(number=5, mode=2, seed=21)  # a one-game session: same kind of game
+    assert pkg.analysis.mcts_distribution(5, 1, mode=2, seed=21)[0].tolist() == [max(pkg.board.get_tiles(one[0])), one[1], one[2]]
+    better = pkg.analysis.mcts_distribution(5, 24, mode=0, seed=3)[:, 1].mean()
+    plain = pkg.analysis.fixed_distribution(4000, seed=3, rows=True)["rows"][:, 1].mean()
+    assert better > 2 * plain  # root search beats blind L,U,D,R play by a wide margin (distribution2.ipynb)
