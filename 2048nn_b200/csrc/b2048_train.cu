@@ -138,37 +138,46 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         bn_bwd_reduce_kernel<<<g4, 256, 0, st>>>((const float4 *)w.da, (const float4 *)gres, (const float4 *)w.a[l],
                                                  (const float4 *)w.z[l], w.stats + l * 256, (float4 *)dybuf, w.part, rows);
         bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, w.grad + P_G(l), w.grad + P_B(l), w.coef + l * 128, 64);
-        uint8_t *dz_img = (mixed == 2 && (l & 1)) ? w.img_dz2 : w.img_dz;
-        if (mixed) {
-            // the weight gradient of layer l+2 read this dz buffer on the side stream: it must be done before the rewrite
-            if (mixed == 2 && l + 2 < NL) CK(cudaStreamWaitEvent(st, g_done[c->device][l + 2], 0));
+        // The weight gradient of layer l runs on a side stream, overlapping the data gradient and the BatchNorm backward
+        // of the layers below; dz (fp32 and image) is double-buffered by layer parity, and the buffer's previous
+        // reader -- the weight gradient of layer l+2 -- must be done before it is rewritten.
+        uint8_t *dz_img = (l & 1) ? w.img_dz2 : w.img_dz;
+        float *dz = (l & 1) ? w.dz2 : w.dz;
+        // (fp32 mode keeps it on the main stream: its FFMA2 weight-gradient and convolution kernels each fill the SMs, and
+        // running them concurrently measured 8 % slower.)
+        const bool forked = mixed != 0;
+        cudaStream_t side = forked ? g_side[c->device] : st;
+        if (forked && l + 2 < NL) CK(cudaStreamWaitEvent(st, g_done[c->device][l + 2], 0));
+        if (mixed)
             bn_bwd_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                               w.coef + l * 128, (float4 *)w.dz, dz_img, n4);
-        } else {
+                                                               w.coef + l * 128, (float4 *)dz, dz_img, n4);
+        else
             bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                         w.coef + l * 128, (float4 *)w.dz, n4);
-        }
-        if (mixed == 2) {  // weight gradient on the tensor cores (bf16 operands), off the critical path
-            cudaStream_t side = g_side[c->device];
+                                                         w.coef + l * 128, (float4 *)dz, n4);
+        if (forked) {
             CK(cudaEventRecord(g_fork[c->device][l], st));
             CK(cudaStreamWaitEvent(side, g_fork[c->device][l], 0));
+        }
+        if (mixed == 2) {  // tensor cores, bf16 operand images
             tc_wgrad_kernel<<<tiles, TCL_THREADS, TCW_SMEM_BYTES, side>>>(w.img_abf[l], dz_img, w.wpart);
             wgrad_reduce_kernel<<<36864 / 64, 256, 0, side>>>(w.wpart, tiles, w.grad + P_W(l), l == 0 ? 16 : 64);
+        } else if (l == 0) {
+            wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), side>>>(w.x0, dz, w.wpart, (long)B, bpc);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, side>>>(w.wpart, splits, w.grad + P_W(0), 16);
+        } else {
+            wgrad_kernel<64><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<64>(), side>>>(w.a[l - 1], dz, w.wpart, (long)B, bpc);
+            wgrad_reduce_kernel<<<36864 / 64, 256, 0, side>>>(w.wpart, splits, w.grad + P_W(l), 64);
+        }
+        if (forked) {
             CK(cudaEventRecord(g_done[c->device][l], side));
             if (l == 0) CK(cudaStreamWaitEvent(st, g_done[c->device][0], 0));  // join: the side stream is in order
-        } else if (l == 0) {
-            wgrad_kernel<16><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<16>(), st>>>(w.x0, w.dz, w.wpart, (long)B, bpc);
-            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(0), 16);
-        } else {
-            wgrad_kernel<64><<<dim3(splits, 3), WG_THREADS, wgrad_smem_bytes<64>(), st>>>(w.a[l - 1], w.dz, w.wpart, (long)B, bpc);
-            wgrad_reduce_kernel<<<36864 / 64, 256, 0, st>>>(w.wpart, splits, w.grad + P_W(l), 64);
         }
         if (l > 0) {
             if (mixed)
                 tc_conv_layer_kernel<true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
                     dz_img, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);
             else
-                conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.dz, w.wd + (size_t)l * 36864, w.da,
+                conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(dz, w.wd + (size_t)l * 36864, w.da,
                                                                                                 nullptr, (long)B);
         }
     }

@@ -42,7 +42,7 @@ constexpr int WGRAD_SPLITS = 98;   // K-splits of the weight-gradient GEMM (x 3 
 struct Workspace {
     float *x0;            // [B][16][16] one-hot input
     float *z[NL], *a[NL];  // pre-BN conv outputs, post-activation outputs
-    float *dyA, *dyB, *dz, *da;
+    float *dyA, *dyB, *dz, *dz2, *da;  // dz double-buffered: the weight gradient reads it on a side stream
     float *z7, *dy7;      // [B][16][4]
     float *h;             // [B][64] head activations, flattened c4*16+p (network.py:85)
     float *dlogits;       // [B][4]
@@ -74,7 +74,8 @@ inline Workspace carve(void *base, int64_t B) {
     };
     w.x0 = take((size_t)B * 16 * 16);
     for (int l = 0; l < NL; l++) w.z[l] = take((size_t)B * ACT), w.a[l] = take((size_t)B * ACT);
-    w.dyA = take((size_t)B * ACT), w.dyB = take((size_t)B * ACT), w.dz = take((size_t)B * ACT), w.da = take((size_t)B * ACT);
+    w.dyA = take((size_t)B * ACT), w.dyB = take((size_t)B * ACT), w.dz = take((size_t)B * ACT), w.dz2 = take((size_t)B * ACT);
+    w.da = take((size_t)B * ACT);
     w.z7 = take((size_t)B * 64), w.dy7 = take((size_t)B * 64);
     w.h = take((size_t)B * 64), w.dlogits = take((size_t)B * 4), w.logp = take((size_t)B * 4);
     w.stats = take(8 * 4 * 64), w.coef = take(8 * 2 * 64);
