@@ -171,3 +171,48 @@ def selfplay(name, model, board=None, number=10, device='cuda', verbose=False, s
     save_record(os.path.join(out_dir, name), rec)
     print('Saved {}.npz'.format(name))
     return rec
+
+
+def main(argv=None):
+    """selfplay.py:118-152: `--seed N` plays main game N (fixed-order min-move search, number=10, times=4, as the
+    reference's default branch) and saves it as selfplay/fixed10/NNNNN.npz.  `--games K` generates K records
+    (seeds N..N+K-1) in one device-resident launch; `--model PATH` switches to the mcts_nn search of selfplay()."""
+    import random
+    from argparse import ArgumentParser
+    from time import time
+
+    parser = ArgumentParser()
+    parser.add_argument('--seed', type=int, default=12345, help='Number to use as seed and save name')
+    parser.add_argument('--verbose', action='store_true', help='Verbose output')
+    parser.add_argument('--games', type=int, default=1, help='records to generate: seeds seed..seed+games-1')
+    parser.add_argument('--model', type=str, default='', help='c64b3 state_dict (.pt): NN-policy search instead of fixed-order')
+    parser.add_argument('--number', type=int, default=10)
+    args = parser.parse_args(argv)
+    if args.seed < 0:
+        raise ValueError('Seed is {}'.format(args.seed))
+    random.seed(args.seed)
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    start_time = time()
+    if args.model:
+        from .network import ConvNet
+        model = ConvNet(channels=64, blocks=3, precision="fp16")
+        model.load_state_dict(torch.load(args.model, map_location="cpu"))
+        model.to('cuda').eval()
+        for k in range(args.games):
+            selfplay(str(args.seed + k).zfill(5), model, number=args.number, verbose=args.verbose, seed=args.seed + k)
+    elif args.games == 1:
+        selfplay_fixed(str(args.seed).zfill(5), number=args.number, times=4, verbose=args.verbose, seed=args.seed)
+    else:
+        print(f'fixed {args.number} lines, 4 times, {args.games} games')
+        recs, _ = selfplay_batch(args.games, args.number, None, 4, seed=args.seed)
+        os.makedirs('selfplay/fixed10/', exist_ok=True)
+        for k, rec in enumerate(recs):
+            save_record(os.path.join('selfplay/fixed10/', str(args.seed + k).zfill(5)), rec)
+        print('Saved {} records, mean score {:.0f}'.format(len(recs), np.mean([r["score"] for r in recs])))
+    total_time = time() - start_time
+    print(f'Took {total_time/60:.1f} minutes')
+
+
+if __name__ == '__main__':
+    main()
