@@ -25,25 +25,32 @@ REFERENCE_PINS = {
 }
 
 
+LOG_FRAC_BITS = 32  # fixed-point scale of acc[16] (b2048_game_summary)
+
+
 def summarize(acc):
-    """acc int64[20] from engine.game_summary -> the notebooks' headline numbers."""
-    a = acc.cpu().numpy().astype(np.int64) if torch.is_tensor(acc) else np.asarray(acc, dtype=np.int64)
-    games = int(a[19])
-    hist = {int(2 ** e): int(a[e]) for e in range(1, 16) if a[e]}
-    return dict(games=games, mean_log_score=float(a[16]) / 2.0 ** 40 / max(games, 1), mean_moves=float(a[17]) / max(games, 1),
-                max_score=int(a[18]), maxtile_hist=hist, frac_2048=float(a[11:16].sum()) / max(games, 1))
+    """acc[20] (tensor from engine.game_summary, or a list of Python ints summed over launches) -> the notebooks'
+    headline numbers."""
+    a = [int(v) for v in (acc.cpu().tolist() if torch.is_tensor(acc) else acc)]
+    games = a[19]
+    hist = {int(2 ** e): a[e] for e in range(1, 16) if a[e]}
+    return dict(games=games, mean_log_score=a[16] / 2.0 ** LOG_FRAC_BITS / max(games, 1), mean_moves=a[17] / max(games, 1),
+                max_score=a[18], maxtile_hist=hist, frac_2048=sum(a[11:16]) / max(games, 1))
 
 
 def _collect(play, n, chunk, rows):
-    acc, out = None, []
+    total, out = [0] * 20, []
+    chunk = min(chunk, 1 << 24)  # one device accumulator per launch; launches are summed in Python integers
     for g0 in range(0, n, chunk):
         m = min(chunk, n - g0)
         final, score, moves = play(g0, m)
-        acc, mt = engine.game_summary(final, score, moves, acc, want_maxtile=rows)
+        acc, mt = engine.game_summary(final, score, moves, None, want_maxtile=rows)
+        part = [int(v) for v in acc.cpu().tolist()]
+        total = [max(a, b) if i == 18 else a + b for i, (a, b) in enumerate(zip(total, part))]
         if rows:
             out.append(torch.stack([mt.to(torch.int64), score.to(torch.int64) & 0xFFFFFFFF, moves.to(torch.int64)], 1).cpu().numpy())
     _raise_if_flag()
-    s = summarize(acc)
+    s = summarize(total)
     if rows:
         s["rows"] = np.concatenate(out)  # distribution.py:12-14: [max(get_tiles(board)), score, moves]
     return s

@@ -189,7 +189,7 @@ __global__ void soft_targets_kernel(const float4 *__restrict__ results, float so
 // Distribution summary of finished games (notebooks/distribution.py:11-14: [max(get_tiles(board)), score, moves]
 // per game, then histograms / mean log score in the notebooks): per-game max tile exponent, and accumulated into
 // `acc` (integer atomics only -> the result does not depend on scheduling):
-//   acc[0..15]  games by max tile exponent      acc[16] sum of round(log10(score+1) * 2^40)
+//   acc[0..15]  games by max tile exponent      acc[16] sum of round(log10(score+1) * 2^32)  (2^32: 2^29 games fit)
 //   acc[17]     sum of moves                    acc[18] max score            acc[19] games
 __global__ void __launch_bounds__(256) game_summary_kernel(const u64 *__restrict__ finals, const u32 *__restrict__ score,
                                                            const u32 *__restrict__ moves, uint8_t *__restrict__ out_maxtile,
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) game_summary_kernel(const u64 *__restrict
         if (out_maxtile) out_maxtile[i] = (uint8_t)m;
         atomicAdd(&s_acc[m], 1ULL);
         const u32 sc = score[i];
-        logsum += (unsigned long long)__double2ll_rn(ldexp(log10((double)sc + 1.0), 40));
+        logsum += (unsigned long long)__double2ll_rn(ldexp(log10((double)sc + 1.0), 32));
         movsum += moves ? moves[i] : 0u;
         best = sc > best ? sc : best;
         games++;

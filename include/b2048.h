@@ -112,7 +112,8 @@ int b2048_soft_targets(b2048_ctx *ctx, const float *results, float soft, float *
 
 /* Distribution summary of n finished games (notebooks/distribution.py:11-14 rows [max tile exponent, score, moves]
  * and the notebooks' histograms / mean log score), ACCUMULATED into acc20 (caller zeroes it):
- *   acc20[0..15] games by max tile exponent, [16] sum of round(log10(score+1) * 2^40), [17] sum of moves,
+ *   acc20[0..15] games by max tile exponent, [16] sum of round(log10(score+1) * 2^32) (no overflow below 2^29 games
+ *   per accumulator), [17] sum of moves,
  *   [18] max score, [19] games.  Integer atomics only: independent of scheduling and of how games are sharded
  *   (ranks add their acc20 vectors, MAX for [18]).  out_maxtile u8[n] and moves may be NULL. */
 int b2048_game_summary(b2048_ctx *ctx, const uint64_t *finals, const uint32_t *score, const uint32_t *moves,

@@ -38,6 +38,9 @@ def test_fixed_order_pin_at_a_million_games(pkg):
     assert lo - 0.012 < s["mean_log_score"] < hi + 0.012
     assert s["frac_2048"] == 0.0 and 512 in s["maxtile_hist"]
     assert 200 < s["mean_moves"] < 250
+    # 16 M games in one accumulator launch + a second chunk: the fixed-point sums must not wrap
+    big = pkg.analysis.fixed_distribution((1 << 24) + 1000, seed=12345)
+    assert big["games"] == (1 << 24) + 1000 and abs(big["mean_log_score"] - s["mean_log_score"]) < 2e-3
     fit = pkg.analysis.weibull_fit(pkg.analysis.fixed_distribution(5000, seed=1, rows=True)["rows"][:, 2], loc=14, scale=200)
     assert 1.0 < fit[0] < 4.0  # shape parameter of the moves distribution (distribution2.ipynb)
 

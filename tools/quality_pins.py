@@ -1,0 +1,23 @@
+"""The reference's published quality pins regenerated at large sample sizes on the B200."""
+import importlib, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+pkg = importlib.import_module("2048nn_b200")
+A = pkg.analysis
+t = time.time()
+s = A.fixed_distribution(1 << 24, seed=12345)
+n = s["games"]
+print(f"fixed-order L,U,D,R: {n} games in {time.time()-t:.2f} s: mean log10(score+1) = {s['mean_log_score']:.5f} "
+      f"(reference, 5000 games each: {A.REFERENCE_PINS['fixed_mean_log_score']}), mean moves {s['mean_moves']:.2f}, max score {s['max_score']}")
+print("  max tile histogram:", {k: f"{v / n * 100:.3f}%" for k, v in sorted(s["maxtile_hist"].items())})
+ng = np.load("tests/golden/c64b3_golden.npz")
+sd = {k[len("sd_shipped/"):]: torch.from_numpy(np.array(ng[k])) for k in ng.files if k.startswith("sd_shipped/")}
+for prec in ("fp16", "fp32"):
+    m = pkg.network.ConvNet(64, 3, precision=prec); m.load_state_dict(sd); m.cuda().eval()
+    N = (1 << 18) if prec == "fp16" else (1 << 14)
+    t = time.time()
+    p = A.policy_distribution(m, N, seed=12345)
+    print(f"shipped c64b3 policy games ({prec}): {N} games in {time.time()-t:.2f} s: mean log10(score+1) = {p['mean_log_score']:.5f} "
+          f"(reference, 5000 games: {A.REFERENCE_PINS['shipped_mean_log_score']}), reached 2048: {p['frac_2048'] * 100:.2f} % "
+          f"(reference: {A.REFERENCE_PINS['shipped_frac_2048'] * 100:.1f} %), mean moves {p['mean_moves']:.1f}, max score {p['max_score']}")
+    print("  max tile histogram:", {k: f"{v / N * 100:.2f}%" for k, v in sorted(p["maxtile_hist"].items())})
