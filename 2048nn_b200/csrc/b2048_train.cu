@@ -23,8 +23,8 @@ static int ensure_attrs(const b2048_ctx *c) {
     CK(cudaFuncSetAttribute(conv3x3_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<16>::BYTES));
     CK(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<64>()));
     CK(cudaFuncSetAttribute(wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad_smem_bytes<16>()));
-    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_conv_layer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_SMEM_BYTES));
     if (c->device >= 64) return b2048_fail_msg("b2048 training: device index above 63");
     CK(cudaStreamCreateWithFlags(&g_side[c->device], cudaStreamNonBlocking));
@@ -91,10 +91,9 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     for (int l = 0; l < NL; l++) {
         const float *res = (l >= 2 && (l & 1) == 0) ? w.a[l - 2] : nullptr;
         if (mixed) {
-            tc_conv_layer_kernel<false><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
-                w.img_a, reinterpret_cast<const uint8_t *>(w.wtc_fwd + (size_t)l * chunk3), w.z[l], (long)B, l == 0 ? 2 : 4);
-            bn_stats_kernel<<<g4, 256, 0, st>>>((const float4 *)w.z[l], w.part, rows);
-            bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
+            tc_conv_layer_kernel<false, true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
+                w.img_a, reinterpret_cast<const uint8_t *>(w.wtc_fwd + (size_t)l * chunk3), w.z[l], w.part, (long)B, l == 0 ? 2 : 4);
+            bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, tiles, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
                                                    run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
             bn_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256,
                                                            (float4 *)w.a[l], w.img_a, l + 1 < NL ? w.img_abf[l + 1] : nullptr, n4);
@@ -174,8 +173,8 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         }
         if (l > 0) {
             if (mixed)
-                tc_conv_layer_kernel<true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
-                    dz_img, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, (long)B, 4);
+                tc_conv_layer_kernel<true, false><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
+                    dz_img, reinterpret_cast<const uint8_t *>(w.wtc_bwd + (size_t)(l - 1) * chunk3), w.da, nullptr, (long)B, 4);
             else
                 conv3x3_kernel<64, false><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(dz, w.wd + (size_t)l * 36864, w.da,
                                                                                                 nullptr, (long)B);

@@ -32,10 +32,16 @@ __device__ __forceinline__ size_t tile_image_offset(int b, int p, int ch) {
     return (size_t)row * tc::ROW_BYTES + (size_t)chunk * 16 + (size_t)(ch & 7) * 2;
 }
 
-template <bool BF16>
+// STATS: per-tile per-channel sum / sum of squares of the outputs (BatchNorm batch statistics) to part[tile][2][64]: the
+// epilogue threads own rows, so the tile is staged in shared memory (the operand image and weights are dead once the
+// accumulators are committed) and summed by columns in a fixed order.
+constexpr int TCL_STAGE_STRIDE = 65;  // floats per staged row: column sums walk consecutive banks
+static_assert((512 * TCL_STAGE_STRIDE + 4 * 2 * 64) * 4 <= TCL_SM_BARS, "the staged tile must fit in the operand region");
+
+template <bool BF16, bool STATS>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
-tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restrict__ wchunks, float *__restrict__ out, long B,
-                     int nk) {
+tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restrict__ wchunks, float *__restrict__ out,
+                     float *__restrict__ part, long B, int nk) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sm_base = tc::smem_u32(sm);
@@ -61,6 +67,7 @@ tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restric
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + TCL_SM_BARS + 16);
+    float *stage = reinterpret_cast<float *>(sm);
 
     if (warp == 4) {
         if (lane == 0) {
@@ -83,21 +90,27 @@ tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restric
         tc::umma_commit_elect(bar_acc);
     } else if (warp < 4) {
         // thread = (board row y = warp, board = lane): TMEM lane y*32 + board, column block x holds position (y, x)
-        tc::mbar_wait(bar_acc, 0);
+        tc::mbar_wait(bar_acc, 0);  // both accumulator halves are committed: every MMA has read its operands
         tc::tc_fence_after();
         const long board = tile * tc::TILE_BOARDS + lane;
+        const bool live = board < B;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int x = 0; x < 4; x++) {
             float *o = out + (board * 16 + warp * 4 + x) * 64;
+            float *srow = stage + (size_t)((x * 4 + warp) * 32 + lane) * TCL_STAGE_STRIDE;
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 float v[8];
                 tc::tmem_ld8(lane_addr + (uint32_t)(x * 64 + c * 8), reinterpret_cast<uint32_t *>(v));
                 tc::tmem_ld_wait();
-                if (board < B) {
+                if (live) {
                     *reinterpret_cast<float4 *>(o + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
                     *reinterpret_cast<float4 *>(o + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (STATS) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) srow[c * 8 + k] = live ? v[k] : 0.f;  // rows past the batch end count as 0
                 }
             }
         }
@@ -106,6 +119,27 @@ tc_conv_layer_kernel(const uint8_t *__restrict__ image, const uint8_t *__restric
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    if (STATS) {
+        // 256 threads = 4 row quarters x 64 channels; quarter sums added in a fixed order
+        float *red = stage + 512 * TCL_STAGE_STRIDE;  // [4][2][64] behind the staged tile
+        const int c = tid & 63, q = tid >> 6;
+        float s1 = 0.f, s2 = 0.f;
+        const float *col = stage + (size_t)(q * 128) * TCL_STAGE_STRIDE + c;
+#pragma unroll 8
+        for (int r = 0; r < 128; r++) {
+            const float v = col[(size_t)r * TCL_STAGE_STRIDE];
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+        }
+        red[(q * 2 + 0) * 64 + c] = s1;
+        red[(q * 2 + 1) * 64 + c] = s2;
+        __syncthreads();
+        if (tid < 128) {
+            const int which = tid >> 6;
+            part[(size_t)tile * 128 + tid] = (red[(0 * 2 + which) * 64 + c] + red[(1 * 2 + which) * 64 + c]) +
+                                             (red[(2 * 2 + which) * 64 + c] + red[(3 * 2 + which) * 64 + c]);
+        }
+    }
 }
 
 // ---- weight gradient on the tensor cores ----------------------------------------------------------------------
@@ -334,29 +368,6 @@ __global__ void pack_weights_tc_kernel(const float *__restrict__ params, uint16_
         const float v = params[P_W(l) + ((k * 64 + n) * 3 + (2 - ky)) * 3 + (2 - kx)];  // n = ci, k = co
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         bwd[dst - (size_t)21 * PER] = *reinterpret_cast<const uint16_t *>(&h);
-    }
-}
-
-// per-channel sum / sum of squares of z (BatchNorm batch statistics) for the tensor-core forward, whose epilogue
-// does not see whole channels: 256 threads = 16 channel quads x 16 row lanes, partials [cta][2][64]
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float4 *__restrict__ z, float *__restrict__ part, long rows) {
-    __shared__ float red[2][16][64];
-    const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (long r = (long)blockIdx.x * 16 + rl; r < rows; r += (long)gridDim.x * 16) {
-        const float4 v = z[r * 16 + cq];
-        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
-        q.x = fmaf(v.x, v.x, q.x), q.y = fmaf(v.y, v.y, q.y), q.z = fmaf(v.z, v.z, q.z), q.w = fmaf(v.w, v.w, q.w);
-    }
-    *reinterpret_cast<float4 *>(&red[0][rl][cq * 4]) = s;
-    *reinterpret_cast<float4 *>(&red[1][rl][cq * 4]) = q;
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-        float t = 0.f;
-#pragma unroll
-        for (int r = 0; r < 16; r++) t += red[which][r][c];
-        part[(size_t)blockIdx.x * 128 + which * 64 + c] = t;
     }
 }
 
