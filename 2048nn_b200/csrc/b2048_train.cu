@@ -66,7 +66,6 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     const double count = (double)rows;
     const float eps = 1e-5f;
     float *run_mean = bn_buffers, *run_var = bn_buffers + 8 * 64;
-    const int ew_grid = cdiv(n4, 256);
 
     const int tiles = cdiv(B, 32);
     const int g4 = 2 * c->num_sms < MAX_PARTS ? 2 * c->num_sms : MAX_PARTS;
@@ -88,15 +87,17 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
     onehot_kernel<<<cdiv(rows, 256), 256, 0, st>>>((const unsigned long long *)boards, w.x0, (long)B);
     // ---- forward (network.py:78-87 in training mode: BatchNorm uses batch statistics) -----------------------
     const int conv_grid = cdiv(B, CONV_BOARDS);
+    const int fat_grid = cdiv(n4, 1024) < c->num_sms ? cdiv(n4, 1024) : c->num_sms;  // finalize + apply kernels: 1024 threads per CTA
     for (int l = 0; l < NL; l++) {
         const float *res = (l >= 2 && (l & 1) == 0) ? w.a[l - 2] : nullptr;
         if (mixed) {
             tc_conv_layer_kernel<false, true><<<tiles, TCL_THREADS, TCL_SMEM_BYTES, st>>>(
                 w.img_a, reinterpret_cast<const uint8_t *>(w.wtc_fwd + (size_t)l * chunk3), w.z[l], w.part, (long)B, l == 0 ? 2 : 4);
-            bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, tiles, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
-                                                   run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
-            bn_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256,
-                                                           (float4 *)w.a[l], w.img_a, l + 1 < NL ? w.img_abf[l + 1] : nullptr, n4);
+            const Image16 im = {w.img_a, l + 1 < NL ? w.img_abf[l + 1] : nullptr};
+            bn_apply_fused_kernel<true><<<fat_grid, 1024, 0, st>>>(w.part, tiles, count, params + P_G(l), params + P_B(l),
+                                                                   run_mean + l * 64, run_var + l * 64, bn_momentum, eps,
+                                                                   w.stats + l * 256, (const float4 *)w.z[l], (const float4 *)res,
+                                                                   (float4 *)w.a[l], im, n4);
             continue;
         }
         if (l == 0)
@@ -104,9 +105,10 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         else
             conv3x3_kernel<64, true><<<conv_grid, CONV_THREADS, ConvSmem<64>::BYTES, st>>>(w.a[l - 1], w.wf + (size_t)l * 36864,
                                                                                            w.z[l], w.part, (long)B);
-        bn_finalize_kernel<<<1, 1024, 0, st>>>(w.part, conv_grid, 128, count, params + P_G(l), params + P_B(l), run_mean + l * 64,
-                                               run_var + l * 64, bn_momentum, eps, w.stats + l * 256, 64);
-        bn_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)w.z[l], (const float4 *)res, w.stats + l * 256, (float4 *)w.a[l], n4);
+        bn_apply_fused_kernel<false><<<fat_grid, 1024, 0, st>>>(w.part, conv_grid, count, params + P_G(l), params + P_B(l),
+                                                                run_mean + l * 64, run_var + l * 64, bn_momentum, eps, w.stats + l * 256,
+                                                                (const float4 *)w.z[l], (const float4 *)res, (float4 *)w.a[l], Image16{},
+                                                                n4);
     }
     float *stats7 = w.stats + 7 * 256, *coef7 = w.coef + 7 * 128;
     const int g1 = cdiv(rows, 256) < MAX_PARTS ? cdiv(rows, 256) : MAX_PARTS;
@@ -136,7 +138,6 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         const float *gres = (even && l != NL - 1) ? w.dyA : nullptr;
         bn_bwd_reduce_kernel<<<g4, 256, 0, st>>>((const float4 *)w.da, (const float4 *)gres, (const float4 *)w.a[l],
                                                  (const float4 *)w.z[l], w.stats + l * 256, (float4 *)dybuf, w.part, rows);
-        bn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(w.part, g4, 128, count, w.grad + P_G(l), w.grad + P_B(l), w.coef + l * 128, 64);
         // The weight gradient of layer l runs on a side stream, overlapping the data gradient and the BatchNorm backward
         // of the layers below; dz (fp32 and image) is double-buffered by layer parity, and the buffer's previous
         // reader -- the weight gradient of layer l+2 -- must be done before it is rewritten.
@@ -148,11 +149,13 @@ extern "C" int b2048_train_forward_backward(b2048_ctx *c, const float *params, f
         cudaStream_t side = forked ? g_side[c->device] : st;
         if (forked && l + 2 < NL) CK(cudaStreamWaitEvent(st, g_done[c->device][l + 2], 0));
         if (mixed)
-            bn_bwd_apply_image_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                               w.coef + l * 128, (float4 *)dz, dz_img, n4);
+            bn_bwd_apply_fused_kernel<true><<<fat_grid, 1024, 0, st>>>(w.part, g4, count, w.grad + P_G(l), w.grad + P_B(l),
+                                                                       w.stats + l * 256, (const float4 *)dybuf, (const float4 *)w.z[l],
+                                                                       (float4 *)dz, Image16{dz_img, nullptr}, n4);
         else
-            bn_bwd_apply_kernel<<<ew_grid, 256, 0, st>>>((const float4 *)dybuf, (const float4 *)w.z[l], w.stats + l * 256,
-                                                         w.coef + l * 128, (float4 *)dz, n4);
+            bn_bwd_apply_fused_kernel<false><<<fat_grid, 1024, 0, st>>>(w.part, g4, count, w.grad + P_G(l), w.grad + P_B(l),
+                                                                        w.stats + l * 256, (const float4 *)dybuf, (const float4 *)w.z[l],
+                                                                        (float4 *)dz, Image16{}, n4);
         if (forked) {
             CK(cudaEventRecord(g_fork[c->device][l], st));
             CK(cudaStreamWaitEvent(side, g_fork[c->device][l], 0));

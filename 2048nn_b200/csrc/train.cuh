@@ -333,20 +333,82 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float *__restri
     run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * count / (count - 1.0));
 }
 
-// a = relu(z*scale + shift (+ res))
-__global__ void bn_apply_kernel(const float4 *__restrict__ z, const float4 *__restrict__ res, const float *__restrict__ stats,
-                                float4 *__restrict__ a, long n4) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c = (int)(i & 15) * 4;
-    const float4 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), sh = *reinterpret_cast<const float4 *>(stats + 192 + c);
-    float4 v = z[i];
-    v.x = fmaf(v.x, sc.x, sh.x), v.y = fmaf(v.y, sc.y, sh.y), v.z = fmaf(v.z, sc.z, sh.z), v.w = fmaf(v.w, sc.w, sh.w);
-    if (res) {
-        const float4 r = res[i];
-        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+// ---- finalize + apply in one launch ----------------------------------------------------------------------------
+// Every CTA (1024 threads) re-reduces the per-CTA partials itself (<= 151 KB from L2, the same fixed order everywhere)
+// instead of waiting for a one-CTA finalize kernel: one launch and one dependency less per layer and direction.
+// CTA 0 publishes the statistics / parameter gradients and updates the running statistics.
+struct Image16 {  // optional 16-bit operand images written next to the fp32 result (mixed mode, train_tc.cuh)
+    uint8_t *img, *img2;
+};
+__device__ __forceinline__ void store_images(const Image16 &im, long i, float4 v, bool first_bf16);
+
+template <bool IMAGE>
+__global__ void __launch_bounds__(1024) bn_apply_fused_kernel(const float *__restrict__ part, int nparts, double count,
+                                                              const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                              float *__restrict__ run_mean, float *__restrict__ run_var, float momentum,
+                                                              float eps, float *__restrict__ stats, const float4 *__restrict__ z,
+                                                              const float4 *__restrict__ res, float4 *__restrict__ a, Image16 im, long n4) {
+    __shared__ __align__(16) float s_sc[64], s_sh[64];
+    double s, q;
+    sum_partials(part, nparts, 128, 64, s, q);
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        const double mean = s / count;
+        double var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float scale = gamma[c] * invstd, shift = beta[c] - (float)mean * scale;
+        s_sc[c] = scale, s_sh[c] = shift;
+        if (blockIdx.x == 0) {
+            stats[c] = (float)mean, stats[64 + c] = invstd, stats[128 + c] = scale, stats[192 + c] = shift;
+            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * count / (count - 1.0));
+        }
     }
-    a[i] = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    __syncthreads();
+    for (long i = (long)blockIdx.x * 1024 + threadIdx.x; i < n4; i += (long)gridDim.x * 1024) {
+        const int c = (int)(i & 15) * 4;
+        const float4 sc = *reinterpret_cast<const float4 *>(s_sc + c), sh = *reinterpret_cast<const float4 *>(s_sh + c);
+        float4 v = z[i];
+        v.x = fmaf(v.x, sc.x, sh.x), v.y = fmaf(v.y, sc.y, sh.y), v.z = fmaf(v.z, sc.z, sh.z), v.w = fmaf(v.w, sc.w, sh.w);
+        if (res) {
+            const float4 r = res[i];
+            v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+        }
+        v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        a[i] = v;
+        if (IMAGE) store_images(im, i, v, false);
+    }
+}
+
+template <bool IMAGE>
+__global__ void __launch_bounds__(1024) bn_bwd_apply_fused_kernel(const float *__restrict__ part, int nparts, double count,
+                                                                  float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                                  const float *__restrict__ stats, const float4 *__restrict__ dy,
+                                                                  const float4 *__restrict__ z, float4 *__restrict__ dz, Image16 im, long n4) {
+    __shared__ __align__(16) float s_c1[64], s_c2[64];
+    double s, q;
+    sum_partials(part, nparts, 128, 64, s, q);
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        s_c1[c] = (float)(s / count), s_c2[c] = (float)(q / count);
+        if (blockIdx.x == 0) dbeta[c] = (float)s, dgamma[c] = (float)q;
+    }
+    __syncthreads();
+    for (long i = (long)blockIdx.x * 1024 + threadIdx.x; i < n4; i += (long)gridDim.x * 1024) {
+        const int c = (int)(i & 15) * 4;
+        const float4 mean = *reinterpret_cast<const float4 *>(stats + c), istd = *reinterpret_cast<const float4 *>(stats + 64 + c),
+                     sc = *reinterpret_cast<const float4 *>(stats + 128 + c), c1 = *reinterpret_cast<const float4 *>(s_c1 + c),
+                     c2 = *reinterpret_cast<const float4 *>(s_c2 + c);
+        const float4 g = dy[i], zv = z[i];
+        float4 o;
+        o.x = sc.x * (g.x - c1.x - (zv.x - mean.x) * istd.x * c2.x);
+        o.y = sc.y * (g.y - c1.y - (zv.y - mean.y) * istd.y * c2.y);
+        o.z = sc.z * (g.z - c1.z - (zv.z - mean.z) * istd.z * c2.z);
+        o.w = sc.w * (g.w - c1.w - (zv.w - mean.w) * istd.w * c2.w);
+        dz[i] = o;
+        if (IMAGE) store_images(im, i, o, true);
+    }
 }
 
 // Backward through ReLU and the BatchNorm reductions: dy = (g1 (+ g2)) * (a > 0); partial sums of dy and dy*xhat
@@ -397,24 +459,6 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float *__re
     dgamma[c] = (float)q;
     coef[c] = (float)(s / count);
     coef[64 + c] = (float)(q / count);
-}
-
-// dz = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))
-__global__ void bn_bwd_apply_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ z, const float *__restrict__ stats,
-                                    const float *__restrict__ coef, float4 *__restrict__ dz, long n4) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c = (int)(i & 15) * 4;
-    const float4 mean = *reinterpret_cast<const float4 *>(stats + c), istd = *reinterpret_cast<const float4 *>(stats + 64 + c),
-                 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), c1 = *reinterpret_cast<const float4 *>(coef + c),
-                 c2 = *reinterpret_cast<const float4 *>(coef + 64 + c);
-    const float4 g = dy[i], zv = z[i];
-    float4 o;
-    o.x = sc.x * (g.x - c1.x - (zv.x - mean.x) * istd.x * c2.x);
-    o.y = sc.y * (g.y - c1.y - (zv.y - mean.y) * istd.y * c2.y);
-    o.z = sc.z * (g.z - c1.z - (zv.z - mean.z) * istd.z * c2.z);
-    o.w = sc.w * (g.w - c1.w - (zv.w - mean.w) * istd.w * c2.w);
-    dz[i] = o;
 }
 
 // ---- weight gradient: dW[tap][ci][co] = sum over (board, position) of a[p+tap][ci] * dz[p][co] ---------------

@@ -300,42 +300,17 @@ __device__ __forceinline__ void store_image4(uint8_t *image, long board, int p, 
     *reinterpret_cast<uint2 *>(image + (size_t)(board >> 5) * TCL_IMG_BYTES + tile_image_offset((int)(board & 31), p, ch)) = w;
 }
 
-// a = relu(z*scale + shift (+ res)) as fp32 and as the next convolution's fp16 operand image
-__global__ void bn_apply_image_kernel(const float4 *__restrict__ z, const float4 *__restrict__ res, const float *__restrict__ stats,
-                                      float4 *__restrict__ a, uint8_t *__restrict__ image, uint8_t *__restrict__ image_bf16, long n4) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c = (int)(i & 15) * 4;
-    const float4 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), sh = *reinterpret_cast<const float4 *>(stats + 192 + c);
-    float4 v = z[i];
-    v.x = fmaf(v.x, sc.x, sh.x), v.y = fmaf(v.y, sc.y, sh.y), v.z = fmaf(v.z, sc.z, sh.z), v.w = fmaf(v.w, sc.w, sh.w);
-    if (res) {
-        const float4 r = res[i];
-        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+// images of the fused finalize+apply kernels (train.cuh): forward = fp16 operand of the next convolution (+ a bf16 copy
+// kept for the weight gradient); backward = bf16 image of dz
+__device__ __forceinline__ void store_images(const Image16 &im, long i, float4 v, bool first_bf16) {
+    const long board = i >> 8;
+    const int p = (int)((i >> 4) & 15), c = (int)(i & 15) * 4;
+    if (first_bf16) {
+        store_image4<true>(im.img, board, p, c, v);
+    } else {
+        store_image4<false>(im.img, board, p, c, v);
+        if (im.img2) store_image4<true>(im.img2, board, p, c, v);
     }
-    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-    a[i] = v;
-    store_image4<false>(image, i >> 8, (int)((i >> 4) & 15), c, v);
-    if (image_bf16) store_image4<true>(image_bf16, i >> 8, (int)((i >> 4) & 15), c, v);  // kept for the weight gradient
-}
-
-// dz = BatchNorm backward of dy, as fp32 (weight gradient) and as the data-gradient convolution's bf16 operand image
-__global__ void bn_bwd_apply_image_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ z, const float *__restrict__ stats,
-                                          const float *__restrict__ coef, float4 *__restrict__ dz, uint8_t *__restrict__ image, long n4) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c = (int)(i & 15) * 4;
-    const float4 mean = *reinterpret_cast<const float4 *>(stats + c), istd = *reinterpret_cast<const float4 *>(stats + 64 + c),
-                 sc = *reinterpret_cast<const float4 *>(stats + 128 + c), c1 = *reinterpret_cast<const float4 *>(coef + c),
-                 c2 = *reinterpret_cast<const float4 *>(coef + 64 + c);
-    const float4 g = dy[i], zv = z[i];
-    float4 o;
-    o.x = sc.x * (g.x - c1.x - (zv.x - mean.x) * istd.x * c2.x);
-    o.y = sc.y * (g.y - c1.y - (zv.y - mean.y) * istd.y * c2.y);
-    o.z = sc.z * (g.z - c1.z - (zv.z - mean.z) * istd.z * c2.z);
-    o.w = sc.w * (g.w - c1.w - (zv.w - mean.w) * istd.w * c2.w);
-    dz[i] = o;
-    store_image4<true>(image, i >> 8, (int)((i >> 4) & 15), c, o);
 }
 
 // ---- weight chunks ------------------------------------------------------------------------------------------
