@@ -127,7 +127,13 @@ __global__ void onehot_kernel(const unsigned long long *__restrict__ boards, flo
 // (100 of 144 tap-positions are in bounds).  The tap's [CIN][64] weight tile streams through a 2-deep cp.async
 // ring.  STATS: per-CTA per-channel sum / sum of squares of the outputs (BatchNorm batch statistics) to
 // part[cta][2][64].
-constexpr int CONV_THREADS = 128, CONV_BOARDS = 8;
+#ifndef B2048_CONV_NQ
+#define B2048_CONV_NQ 2
+#endif
+constexpr int CONV_NQ = B2048_CONV_NQ;            // float4 channel groups per thread: 2 -> 8x8 register tile, 4 -> 8x16
+constexpr int CONV_THREADS = 256 / CONV_NQ, CONV_BOARDS = 8;
+constexpr int CONV_CGS = 16 / CONV_NQ;             // threads along the 64 output channels
+constexpr int CONV_CSTRIDE = 64 / CONV_NQ;         // channel distance between a thread's groups
 template <int CIN>
 struct ConvSmem {
     static constexpr int PIXC = CIN + 4;          // floats per position (+4 keeps 16-byte alignment, spreads banks)
@@ -147,7 +153,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // one tap for the rows in MASK (bit i: output row i = (y0 + i/4, i%4) has its input position on the board)
 template <int CIN, int MASK>
-__device__ __forceinline__ void conv_tap(const float *ap, const float *wt, float2 (&acc)[8][4]) {
+__device__ __forceinline__ void conv_tap(const float *ap, const float *wt, float2 (&acc)[8][2 * CONV_NQ]) {
     constexpr int PIXC = ConvSmem<CIN>::PIXC;
 #pragma unroll 2
     for (int c4 = 0; c4 < CIN / 4; c4++) {
@@ -157,18 +163,18 @@ __device__ __forceinline__ void conv_tap(const float *ap, const float *wt, float
             if ((MASK >> i) & 1) av[i] = *reinterpret_cast<const float4 *>(ap + ((i >> 2) * 4 + (i & 3)) * PIXC + c4 * 4);
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + kk) * 64);
-            const float4 w1 = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + kk) * 64 + 32);
-            const float2 w00 = make_float2(w0.x, w0.y), w01 = make_float2(w0.z, w0.w), w10 = make_float2(w1.x, w1.y),
-                         w11 = make_float2(w1.z, w1.w);
+            float2 w[2 * CONV_NQ];
+#pragma unroll
+            for (int j = 0; j < CONV_NQ; j++) {
+                const float4 t = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + kk) * 64 + j * CONV_CSTRIDE);
+                w[2 * j] = make_float2(t.x, t.y), w[2 * j + 1] = make_float2(t.z, t.w);
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if (!((MASK >> i) & 1)) continue;
                 const float a = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
-                acc[i][0] = ffma2(a, w00, acc[i][0]);
-                acc[i][1] = ffma2(a, w01, acc[i][1]);
-                acc[i][2] = ffma2(a, w10, acc[i][2]);
-                acc[i][3] = ffma2(a, w11, acc[i][3]);
+#pragma unroll
+                for (int j = 0; j < 2 * CONV_NQ; j++) acc[i][j] = ffma2(a, w[j], acc[i][j]);
             }
         }
     }
@@ -201,13 +207,13 @@ __global__ void __launch_bounds__(CONV_THREADS) conv3x3_kernel(const float *__re
         }
     }
     const int warp = tid >> 5, lane = tid & 31;
-    const int half = warp & 1, b = (warp >> 1) * 4 + (lane >> 3), cg = lane & 7;
+    const int half = warp & 1, b = (warp >> 1) * (32 / CONV_CGS) + lane / CONV_CGS, cg = lane % CONV_CGS;
     const int y0 = half * 2;
-    float2 acc[8][4];
+    float2 acc[8][2 * CONV_NQ];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < 2 * CONV_NQ; j++) acc[i][j] = make_float2(0.f, 0.f);
 
 #pragma unroll
     for (int tap = 0; tap < 9; tap++) {
@@ -247,39 +253,35 @@ __global__ void __launch_bounds__(CONV_THREADS) conv3x3_kernel(const float *__re
     if (b < nb) {
         float *o = out + ((base + b) * 16 + y0 * 4) * 64 + cg * 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            *reinterpret_cast<float4 *>(o + i * 64) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
-            *reinterpret_cast<float4 *>(o + i * 64 + 32) = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
-        }
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < CONV_NQ; j++)
+                *reinterpret_cast<float4 *>(o + i * 64 + j * CONV_CSTRIDE) =
+                    make_float4(acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y);
     }
     if (STATS) {
-        float s[8], q[8];
+        // red[0][rg][64], red[1][rg][64] with rg = (board, half); pair j of a thread = channels 4cg + (j/2)*CSTRIDE + 2*(j%2) + {0,1}
+        const int rg = b * 2 + half;
+        __syncthreads();  // every thread is done reading the input tile
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 2 * CONV_NQ; j++) {
             float sx = 0.f, sy = 0.f, qx = 0.f, qy = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 sx += acc[i][j].x, sy += acc[i][j].y;
                 qx = fmaf(acc[i][j].x, acc[i][j].x, qx), qy = fmaf(acc[i][j].y, acc[i][j].y, qy);
             }
-            s[2 * j] = sx, s[2 * j + 1] = sy, q[2 * j] = qx, q[2 * j + 1] = qy;
-        }
-        // red[0][rg][64], red[1][rg][64] with rg = (board, half); channel of slot k: (k < 4 ? 4cg + k : 32 + 4cg + k - 4)
-        const int rg = b * 2 + half;
-        __syncthreads();  // every thread is done reading the input tile
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c = (k < 4) ? cg * 4 + k : 32 + cg * 4 + (k - 4);
-            red[rg * 64 + c] = s[k];
-            red[16 * 64 + rg * 64 + c] = q[k];
+            const int c = cg * 4 + (j >> 1) * CONV_CSTRIDE + 2 * (j & 1);
+            red[rg * 64 + c] = sx, red[rg * 64 + c + 1] = sy;
+            red[16 * 64 + rg * 64 + c] = qx, red[16 * 64 + rg * 64 + c + 1] = qy;
         }
         __syncthreads();
-        {
-            const int which = tid >> 6, c = tid & 63;
-            float t = 0.f;
+        for (int t = tid; t < 128; t += CONV_THREADS) {
+            const int which = t >> 6, c = t & 63;
+            float v = 0.f;
 #pragma unroll
-            for (int r = 0; r < 16; r++) t += red[which * 16 * 64 + r * 64 + c];
-            part[(size_t)blockIdx.x * 128 + which * 64 + c] = t;
+            for (int r = 0; r < 16; r++) v += red[which * 16 * 64 + r * 64 + c];
+            part[(size_t)blockIdx.x * 128 + which * 64 + c] = v;
         }
     }
 }
