@@ -152,7 +152,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     blob = m.blob("fp16")
     G, number = args.nn_origins * world, args.nn_lines
     origins = eng.init_boards(G, 4242, 0)  # synthetic fresh start boards, same on every rank
-    for w in range(2):
+    for w in range(max(3, args.warmup)):
         d.mcts_nn_sharded(blob, "fp16", origins, number, 100 + w, 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
