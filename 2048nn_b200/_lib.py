@@ -29,6 +29,7 @@ _SIGS = {
     "b2048_create": (C.c_int, [C.c_int, C.POINTER(P)]),
     "b2048_destroy": (C.c_int, [P]),
     "b2048_num_sms": (C.c_int, [P]),
+    "b2048_launch_count": (i64, [P]),
     "b2048_set_playout_variant": (C.c_int, [P, C.c_int]),
     "b2048_take_error_flag": (C.c_int, [P, P, C.POINTER(C.c_int)]),
     "b2048_tables": (C.c_int, [P, P, P, P, P, P, P]),
@@ -48,6 +49,8 @@ _SIGS = {
     "b2048_playout_nn_population": (C.c_int, [P, C.c_int, P, i64, C.c_int, P, u64, u64, u64, C.c_int, P, P, P, P, P, i64, P]),
     "b2048_mcts_nn": (C.c_int, [P, C.c_int, P, P, i64, C.c_int, C.c_int, C.c_int, u64, u64, P, P, P, P, P, P]),
     "b2048_selfplay_fixed": (C.c_int, [P, P, i64, u64, u64, C.c_int, C.c_int, C.c_int, u64, C.c_int, P, P, P, P, P, P, P, P]),
+    "b2048_selfplay_nn_workspace_bytes": (i64, [i64, C.c_int]),
+    "b2048_selfplay_nn": (C.c_int, [P, C.c_int, P, P, i64, u64, u64, C.c_int, u64, C.c_int, P, P, P, P, P, P, P, P, P]),
     "b2048_game_summary": (C.c_int, [P, P, P, P, P, P, i64, P]),
     "b2048_train_workspace_bytes": (i64, [i64]),
     "b2048_train_grad_offset": (i64, [i64]),
@@ -105,6 +108,11 @@ def ctx(device=None):
         check(lib.b2048_create(dev, C.byref(h)))
         _ctx[dev] = h
     return _ctx[dev]
+
+
+def launch_count(device=None):
+    """Kernels launched through the device's context so far (b2048_launch_count)."""
+    return int(load_library().b2048_launch_count(ctx(device)))
 
 
 def stream_ptr(device=None):

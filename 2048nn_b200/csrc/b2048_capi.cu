@@ -41,13 +41,17 @@ extern "C" const char *b2048_last_error(void) { return g_err; }
 
 extern "C" int b2048_create(int device, b2048_ctx **out) {
     if (!out) return fail_msg("b2048_create: out is NULL");
-    CK(cudaSetDevice(device));
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail_msg("b2048_create: no such CUDA device");
+    DeviceGuard dg(device);  // the caller's current device is restored on return
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail_msg("b2048_create: this library is built for sm_100a (Blackwell) only");
     b2048_ctx *c = new b2048_ctx();
-    memset(c, 0, sizeof *c);
     c->device = device;
+    c->next_counter = 0;
+    c->launches = 0;
     c->num_sms = prop.multiProcessorCount;
     CK(cudaMalloc(&c->fin_fwd, 65536 * sizeof(uint16_t)));
     CK(cudaMalloc(&c->fin_rev, 65536 * sizeof(uint16_t)));
@@ -58,9 +62,10 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
     c->k2_variant = 1;
     CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
+    CK(cudaMemset(c->counters, 0, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
     CK(cudaMemset(c->err_flag, 0, 2 * sizeof(int)));
-    build_tables_kernel<<<65536 / 256, 256>>>(c->fin_fwd, c->fin_rev, c->score, c->moved_fwd, c->moved_rev,
+    build_tables_kernel<<<LC(c, 65536 / 256), 256>>>(c->fin_fwd, c->fin_rev, c->score, c->moved_fwd, c->moved_rev,
                                               c->legal, c->rowstat, c->err_flag + 1);
     CK(cudaGetLastError());
     int mism = 0;
@@ -78,6 +83,8 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -89,7 +96,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
 
 extern "C" int b2048_destroy(b2048_ctx *c) {
     if (!c) return 0;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaFree(c->fin_fwd);
     cudaFree(c->fin_rev);
     cudaFree(c->score);
@@ -99,22 +106,23 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
     cudaFree(c->rowstat);
     cudaFree(c->counters);
     cudaFree(c->err_flag);
-    cudaFree(c->rboard);
     delete c;
     return 0;
 }
 
 extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
+extern "C" int64_t b2048_launch_count(const b2048_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
 
 extern "C" int b2048_set_playout_variant(b2048_ctx *c, int variant) {
     if (variant != 0 && variant != 1) return fail_msg("b2048_set_playout_variant: variant must be 0 or 1");
-    c->k2_variant = variant;
+    c->k2_variant.store(variant);
     return 0;
 }
 
 /* device error flag: set when a spawn hit countzero == 0 (ValueError in the reference).
  * Reads and clears it; synchronises `stream`. */
 extern "C" int b2048_take_error_flag(b2048_ctx *c, void *stream, int *out) {
+    DeviceGuard dg(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(out, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -131,6 +139,7 @@ static inline int grid_for(long n, int threads, int cap) {
 
 extern "C" int b2048_tables(b2048_ctx *c, uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score,
                             uint8_t *moved_fwd, uint8_t *moved_rev, void *stream) {
+    DeviceGuard dg(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (fin_fwd) CK(cudaMemcpyAsync(fin_fwd, c->fin_fwd, 65536 * 2, cudaMemcpyDeviceToDevice, st));
     if (fin_rev) CK(cudaMemcpyAsync(fin_rev, c->fin_rev, 65536 * 2, cudaMemcpyDeviceToDevice, st));
@@ -143,8 +152,9 @@ extern "C" int b2048_tables(b2048_ctx *c, uint16_t *fin_fwd, uint16_t *fin_rev, 
 extern "C" int b2048_move_batch(b2048_ctx *c, const uint64_t *boards, const uint8_t *dirs, int dir_scalar,
                                 uint64_t *out_boards, uint32_t *out_score, uint8_t *out_moved, int64_t n,
                                 void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
-    move_batch_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    move_batch_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         tables_of(c), (const u64 *)boards, dirs, dir_scalar, (u64 *)out_boards, out_score, out_moved, (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -152,8 +162,9 @@ extern "C" int b2048_move_batch(b2048_ctx *c, const uint64_t *boards, const uint
 
 extern "C" int b2048_board_ops(b2048_ctx *c, const uint64_t *boards, uint64_t *out_transpose,
                                uint8_t *out_countzero, uint8_t *out_legal_mask, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
-    board_ops_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    board_ops_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         tables_of(c), (const u64 *)boards, (u64 *)out_transpose, out_countzero, out_legal_mask, (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -161,8 +172,9 @@ extern "C" int b2048_board_ops(b2048_ctx *c, const uint64_t *boards, uint64_t *o
 
 extern "C" int b2048_init_boards(b2048_ctx *c, uint64_t seed, uint64_t gid_base, uint64_t *out_boards,
                                  int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
-    init_boards_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    init_boards_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         seed, gid_base, (u64 *)out_boards, (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -171,8 +183,9 @@ extern "C" int b2048_init_boards(b2048_ctx *c, uint64_t seed, uint64_t gid_base,
 extern "C" int b2048_spawn_batch(b2048_ctx *c, const uint64_t *boards, uint64_t seed, const uint64_t *gids,
                                  uint64_t gid_base, const uint32_t *k, uint32_t k_scalar, uint64_t *out_boards,
                                  int32_t *err_flag, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
-    spawn_batch_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    spawn_batch_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         (const u64 *)boards, seed, (const u64 *)gids, gid_base, k, k_scalar, (u64 *)out_boards, err_flag,
         (long)n);
     CK(cudaGetLastError());
@@ -181,8 +194,9 @@ extern "C" int b2048_spawn_batch(b2048_ctx *c, const uint64_t *boards, uint64_t 
 
 extern "C" int b2048_rng_draws(b2048_ctx *c, uint64_t seed, uint64_t gid_base, uint64_t first, int count,
                                uint64_t *out, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0 || count <= 0) return 0;
-    rng_draws_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    rng_draws_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         seed, gid_base, first, count, (u64 *)out, (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -191,10 +205,11 @@ extern "C" int b2048_rng_draws(b2048_ctx *c, uint64_t seed, uint64_t gid_base, u
 extern "C" int b2048_policy_step(b2048_ctx *c, const uint64_t *boards, const uint8_t *prio, uint64_t seed,
                                  const uint64_t *gids, uint64_t gid_base, const uint32_t *k, uint64_t *out_boards,
                                  uint32_t *out_gain, uint8_t *out_moved, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     if (!boards || !prio || !k || !out_boards || !out_gain || !out_moved)
         return fail_msg("b2048_policy_step: NULL argument");
-    policy_step_kernel<<<grid_for(n, 256, c->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+    policy_step_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 16)), 256, 0, (cudaStream_t)stream>>>(
         tables_of(c), (const u64 *)boards, prio, seed, (const u64 *)gids, gid_base, k, (u64 *)out_boards, out_gain,
         out_moved, c->err_flag, (long)n);
     CK(cudaGetLastError());
@@ -202,18 +217,20 @@ extern "C" int b2048_policy_step(b2048_ctx *c, const uint64_t *boards, const uin
 }
 
 extern "C" int b2048_encode_boards(b2048_ctx *c, const uint64_t *boards, int mode, float *out, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     if (mode != 0 && mode != 1) return fail_msg("b2048_encode_boards: mode must be 0 (exponents) or 1 (one-hot)");
     const long total = (long)n * (mode ? 64 : 4);
-    encode_boards_kernel<<<grid_for(total, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+    encode_boards_kernel<<<LC(c, grid_for(total, 256, c->num_sms * 8)), 256, 0, (cudaStream_t)stream>>>(
         (const u64 *)boards, mode, reinterpret_cast<float4 *>(out), (long)n);
     CK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int b2048_soft_targets(b2048_ctx *c, const float *results, float soft, float *out, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
-    soft_targets_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+    soft_targets_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 8)), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(results), soft, reinterpret_cast<float4 *>(out), (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -221,20 +238,19 @@ extern "C" int b2048_soft_targets(b2048_ctx *c, const float *results, float soft
 
 extern "C" int b2048_game_summary(b2048_ctx *c, const uint64_t *finals, const uint32_t *score, const uint32_t *moves,
                                   uint8_t *out_maxtile, uint64_t *acc20, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     if (!finals || !score || !acc20) return fail_msg("b2048_game_summary: NULL argument");
-    game_summary_kernel<<<grid_for(n, 256, c->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+    game_summary_kernel<<<LC(c, grid_for(n, 256, c->num_sms * 8)), 256, 0, (cudaStream_t)stream>>>(
         (const u64 *)finals, score, moves, out_maxtile, (unsigned long long *)acc20, (long)n);
     CK(cudaGetLastError());
     return 0;
 }
 
-static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st);
 static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
     p.tb = tables_of(c);
     p.err_flag = c->err_flag;
-    unsigned slot = (c->next_counter++) % N_COUNTERS;
-    p.counter = c->counters + slot;
+    p.counter = take_counters(c, 1);
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
     // one CTA per SM; fewer games than 1024 x #SMs are spread over all SMs with narrower CTAs instead of filling a few
     // SMs (the kernels take their stride from blockDim): 64 K games = 148 x 448 threads rather than 64 x 1024
@@ -246,15 +262,15 @@ static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
         grid = (int)((p.n + block - 1) / block);
     }
     bool ludr = p.order[0] == 0 && p.order[1] == 1 && p.order[2] == 3 && p.order[3] == 2;
-    if (c->k2_variant == 1) {
+    if (c->k2_variant.load() == 1) {
         if (ludr)
-            playout_fixed_kernel2<true><<<grid, block, K2V2_SMEM_BYTES, st>>>(p);
+            playout_fixed_kernel2<true><<<LC(c, grid), block, K2V2_SMEM_BYTES, st>>>(p);
         else
-            playout_fixed_kernel2<false><<<grid, block, K2V2_SMEM_BYTES, st>>>(p);
+            playout_fixed_kernel2<false><<<LC(c, grid), block, K2V2_SMEM_BYTES, st>>>(p);
     } else if (ludr) {
-        playout_fixed_kernel<true><<<grid, block, 131072, st>>>(p);
+        playout_fixed_kernel<true><<<LC(c, grid), block, 131072, st>>>(p);
     } else {
-        playout_fixed_kernel<false><<<grid, block, 131072, st>>>(p);
+        playout_fixed_kernel<false><<<LC(c, grid), block, 131072, st>>>(p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -263,6 +279,7 @@ static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
 extern "C" int b2048_playout_fixed(b2048_ctx *c, const uint64_t *start, const uint8_t *order4_host,
                                    uint64_t seed, uint64_t gid_base, uint32_t spawn0, uint64_t *out_final,
                                    uint32_t *out_score, uint32_t *out_moves, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     PlayParams p;
     memset(&p, 0, sizeof p);
@@ -283,20 +300,20 @@ extern "C" int b2048_mcts_fixed(b2048_ctx *c, const uint64_t *origins, int64_t G
                                 int line_end, uint64_t seed, uint64_t eval_id_base, uint8_t *out_legal,
                                 uint32_t *out_rscore, uint32_t *out_lscore, uint32_t *out_lmoves,
                                 int64_t *out_logsum, int32_t *out_count, int32_t *out_minmov, void *stream) {
+    DeviceGuard dg(c->device);
     if (G <= 0) return 0;
     if (number <= 0 || line_begin < 0 || line_end > number || line_begin > line_end)
         return fail_msg("b2048_mcts_fixed: bad line range");
     if (!out_legal || !out_rscore) return fail_msg("b2048_mcts_fixed: out_legal and out_rscore are required");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ensure_rboard(c, G, st)) return rc;
-    root_moves_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
-                                                                       out_legal, out_rscore, (u64 *)c->rboard);
+    root_moves_kernel<<<LC(c, (unsigned)((G * 4 + 255) / 256)), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
+                                                                       out_legal, out_rscore);
     CK(cudaGetLastError());
     if (line_begin == line_end) return 0;
     PlayParams p;
     memset(&p, 0, sizeof p);
     p.root_mode = 1;
-    p.rboard = (const u64 *)c->rboard;
+    p.origins = (const u64 *)origins;
     p.rlegal = out_legal;
     p.rscore = out_rscore;
     p.number = number;
@@ -319,6 +336,7 @@ extern "C" int b2048_selfplay_fixed(b2048_ctx *c, const uint64_t *starts, int64_
                                     uint64_t games_total, int number, int times, int mode, uint64_t seed, int max_steps,
                                     uint64_t *out_boards, float *out_results, uint64_t *out_final, int64_t *out_score,
                                     int32_t *out_steps, int32_t *out_status, uint64_t *move_counter, void *stream) {
+    DeviceGuard dg(c->device);
     if (G <= 0) return 0;
     if (number <= 0 || times <= 0 || times > SELFPLAY_MAX_TIMES || max_steps <= 0)
         return fail_msg("b2048_selfplay_fixed: need number > 0, 1 <= times <= 64, max_steps > 0");
@@ -348,7 +366,7 @@ extern "C" int b2048_selfplay_fixed(b2048_ctx *c, const uint64_t *starts, int64_
     long lines = (long)times * 4 * number;
     int threads = (int)(lines < 1024 ? ((lines + 31) / 32) * 32 : 1024);
     size_t smem = mode == B2048_MODE_MEDIAN ? (size_t)16 * number : 0;
-    selfplay_fixed_kernel<<<(unsigned)G, threads, smem, (cudaStream_t)stream>>>(p);
+    selfplay_fixed_kernel<<<LC(c, (unsigned)G), threads, smem, (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return 0;
 }
@@ -362,17 +380,6 @@ extern "C" int64_t b2048_convnet_blob_bytes(int precision) {
     return -1;
 }
 
-static int ensure_rboard(b2048_ctx *c, int64_t G, cudaStream_t st) {
-    if (c->rboard_cap < G * 4) {
-        CK(cudaStreamSynchronize(st));
-        cudaFree(c->rboard);
-        int64_t cap = G * 4 < 4096 ? 4096 : G * 4;
-        CK(cudaMalloc(&c->rboard, cap * sizeof(uint64_t)));
-        c->rboard_cap = cap;
-    }
-    return 0;
-}
-
 static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logp, float *out_logits,
                              float *dbg, int dbg_layer, int64_t n, cudaStream_t st, bool bf16 = false) {
     tc::FwdWork::Params p;
@@ -380,18 +387,17 @@ static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boa
     p.out_logp = out_logp;
     p.out_logits = out_logits;
     p.n = (long)n;
-    unsigned slot = (c->next_counter++) % N_COUNTERS;
-    p.counter = c->counters + slot;
+    p.counter = take_counters(c, 1);
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
     int grid = grid_for(n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
     if (dbg)
-        tc::tc_persistent_kernel<tc::FwdWork, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+        tc::tc_persistent_kernel<tc::FwdWork, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, dbg, dbg_layer, (long)n);
     else if (bf16)
-        tc::tc_persistent_kernel<tc::FwdWork, false, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+        tc::tc_persistent_kernel<tc::FwdWork, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, nullptr, -1, (long)n);
     else
-        tc::tc_persistent_kernel<tc::FwdWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+        tc::tc_persistent_kernel<tc::FwdWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, nullptr, -1, (long)n);
     CK(cudaGetLastError());
     return 0;
@@ -399,12 +405,13 @@ static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boa
 
 extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *blob, const uint64_t *boards,
                                      float *out_logp, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     if (!blob || !boards || !out_logp) return fail_msg("b2048_convnet_forward: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == B2048_PREC_FP32) {
         int grid = grid_for(n, CN_BOARDS_PER_CTA, c->num_sms * 2);
-        convnet_fp32_forward_kernel<<<grid, 512, CN_FP32_SMEM_BYTES, st>>>((const float *)blob, (const u64 *)boards,
+        convnet_fp32_forward_kernel<<<LC(c, grid), 512, CN_FP32_SMEM_BYTES, st>>>((const float *)blob, (const u64 *)boards,
                                                                            out_logp, (long)n);
         CK(cudaGetLastError());
         return 0;
@@ -418,6 +425,7 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
  * fp32 post-activation output of conv layer `dbg_layer` (0..6) as [board][64 co][16 pos]. */
 extern "C" int b2048_convnet_tc_debug(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logits,
                                       float *dbg, int dbg_layer, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     return launch_tc_forward(c, blob, boards, nullptr, out_logits, dbg, dbg ? dbg_layer : -1, n, (cudaStream_t)stream);
 }
@@ -428,15 +436,12 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
     const int models = p.n_models > 1 ? p.n_models : 1;
     if (models > N_COUNTERS || models > c->num_sms) return fail_msg("b2048 NN playout: too many models in one launch");
     // `models` consecutive work cursors out of the rotating pool
-    unsigned slot = c->next_counter % N_COUNTERS;
-    if (slot + (unsigned)models > N_COUNTERS) slot = 0;
-    c->next_counter = slot + (unsigned)models;
-    p.counter = c->counters + slot;
+    p.counter = take_counters(c, (unsigned)models);
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * models, st));
     const long total = p.n * models;
     if (precision == B2048_PREC_FP32) {
         int grid = models > 1 ? c->num_sms * 2 : grid_for(p.n, CN_BOARDS_PER_CTA, c->num_sms * 2);
-        playout_nn_fp32_kernel<<<grid, 512, CN_FP32_SMEM_BYTES, st>>>(p);
+        playout_nn_fp32_kernel<<<LC(c, grid), 512, CN_FP32_SMEM_BYTES, st>>>(p);
         CK(cudaGetLastError());
         return 0;
     }
@@ -452,11 +457,15 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
             grid = p.single_set ? grid_for(total, tc::TILE_BOARDS, c->num_sms)
                                 : grid_for(total, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
         }
-        if (precision == B2048_PREC_BF16_TC)
-            tc::tc_persistent_kernel<PlayWork, false, true><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+        if (p.main_mode) {
+            if (precision != B2048_PREC_FP16_TC) return fail_msg("b2048_selfplay_nn: precision must be FP32 or FP16_TC");
+            tc::tc_persistent_kernel<MainWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        } else if (precision == B2048_PREC_BF16_TC)
+            tc::tc_persistent_kernel<PlayWork, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
         else
-            tc::tc_persistent_kernel<PlayWork, false><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            tc::tc_persistent_kernel<PlayWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
         CK(cudaGetLastError());
         return 0;
@@ -468,6 +477,7 @@ extern "C" int b2048_playout_nn(b2048_ctx *c, int precision, const void *blob, c
                                 uint64_t gid_base, uint32_t spawn0, int group_size, int32_t *group_min,
                                 uint64_t *out_final, uint32_t *out_score, uint32_t *out_moves,
                                 uint64_t *move_counter, int64_t n, void *stream) {
+    DeviceGuard dg(c->device);
     if (n <= 0) return 0;
     if (!blob) return fail_msg("b2048_playout_nn: blob is NULL");
     NNPlayParams p;
@@ -492,6 +502,7 @@ extern "C" int b2048_playout_nn_population(b2048_ctx *c, int precision, const vo
                                            uint64_t gid_model_stride, int group_size, int32_t *group_min,
                                            uint64_t *out_final, uint32_t *out_score, uint32_t *out_moves,
                                            uint64_t *move_counter, int64_t n_per_model, void *stream) {
+    DeviceGuard dg(c->device);
     if (n_per_model <= 0 || n_models <= 0) return 0;
     if (!blobs) return fail_msg("b2048_playout_nn_population: blobs is NULL");
     if (blob_stride <= 0 || (blob_stride & 15)) return fail_msg("b2048_playout_nn_population: blob_stride must be a positive multiple of 16");
@@ -527,21 +538,21 @@ extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, cons
                              int number, int line_begin, int line_end, uint64_t seed, uint64_t eval_id_base,
                              uint8_t *out_legal, uint32_t *out_rscore, uint32_t *out_lmoves, int32_t *out_minmov,
                              uint64_t *move_counter, void *stream) {
+    DeviceGuard dg(c->device);
     if (G <= 0) return 0;
     if (number <= 0 || line_begin < 0 || line_end > number || line_begin > line_end)
         return fail_msg("b2048_mcts_nn: bad line range");
     if (!blob || !out_legal || !out_rscore || !out_minmov) return fail_msg("b2048_mcts_nn: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ensure_rboard(c, G, st)) return rc;
-    root_moves_kernel<<<(unsigned)((G * 4 + 255) / 256), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
-                                                                       out_legal, out_rscore, (u64 *)c->rboard);
+    root_moves_kernel<<<LC(c, (unsigned)((G * 4 + 255) / 256)), 256, 0, st>>>(tables_of(c), (const u64 *)origins, (long)G,
+                                                                       out_legal, out_rscore);
     CK(cudaGetLastError());
     if (line_begin == line_end) return 0;
     NNPlayParams p;
     memset(&p, 0, sizeof p);
     p.blob = blob;
     p.root_mode = 1;
-    p.rboard = (const u64 *)c->rboard;
+    p.origins = (const u64 *)origins;
     p.rlegal = out_legal;
     p.number = number;
     p.line_begin = line_begin;
@@ -553,6 +564,73 @@ extern "C" int b2048_mcts_nn(b2048_ctx *c, int precision, const void *blob, cons
     p.group_min = out_minmov;
     p.out_moves = out_lmoves;
     p.move_counter = (unsigned long long *)move_counter;
+    return launch_nn(c, precision, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-resident NN main games (selfplay.py:62-115 driven by mcts_nn.py:4-43)
+// ------------------------------------------------------------------------------------------
+static inline uint32_t mg_ring_cap(int64_t G, int number) {
+    uint64_t need = 2ULL * (uint64_t)G * 4ULL * (uint64_t)number;
+    uint32_t cap = 1024;
+    while ((uint64_t)cap < need) cap <<= 1;
+    return cap;
+}
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int64_t b2048_selfplay_nn_workspace_bytes(int64_t G, int number) {
+    if (G <= 0 || number <= 0 || (uint64_t)G * 4ULL * (uint64_t)number >= (1ULL << 30)) return -1;
+    return (int64_t)(align256(sizeof(MainQueue)) + align256((size_t)G * sizeof(MainGame)) + align256((size_t)G * 4 * sizeof(int)) +
+                     (size_t)mg_ring_cap(G, number) * sizeof(uint32_t));
+}
+
+extern "C" int b2048_selfplay_nn(b2048_ctx *c, int precision, const void *blob, const uint64_t *starts, int64_t G,
+                                 uint64_t game_id_base, uint64_t games_total, int number, uint64_t seed, int max_steps,
+                                 uint64_t *out_boards, float *out_results, uint64_t *out_final, int64_t *out_score,
+                                 int32_t *out_steps, int32_t *out_status, uint64_t *move_counter, void *workspace,
+                                 void *stream) {
+    DeviceGuard dg(c->device);
+    if (G <= 0) return 0;
+    if (!blob || !workspace) return fail_msg("b2048_selfplay_nn: blob and workspace are required");
+    if (number <= 0 || max_steps < 0) return fail_msg("b2048_selfplay_nn: need number > 0, max_steps >= 0");
+    if (!out_final || !out_score || !out_steps || !out_status) return fail_msg("b2048_selfplay_nn: NULL output");
+    if (games_total < game_id_base + (uint64_t)G) return fail_msg("b2048_selfplay_nn: games_total < game_id_base + G");
+    const int64_t wbytes = b2048_selfplay_nn_workspace_bytes(G, number);
+    if (wbytes < 0) return fail_msg("b2048_selfplay_nn: G * 4 * number too large");
+    if ((uintptr_t)workspace & 255) return fail_msg("b2048_selfplay_nn: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    NNPlayParams p;
+    memset(&p, 0, sizeof p);
+    uint8_t *w = (uint8_t *)workspace;
+    p.mgq = (MainQueue *)w;
+    w += align256(sizeof(MainQueue));
+    p.mg = (MainGame *)w;
+    w += align256((size_t)G * sizeof(MainGame));
+    p.group_min = (int *)w;
+    w += align256((size_t)G * 4 * sizeof(int));
+    p.mg_items = (uint32_t *)w;
+    p.mg_cap = mg_ring_cap(G, number);
+    CK(cudaMemsetAsync(workspace, 0, (size_t)wbytes, st));
+    p.main_mode = 1;
+    p.blob = blob;
+    p.n = (long)G * 4 * number;  // lines in flight at most (launch sizing only)
+    p.number = number;
+    p.seed = seed;
+    p.spawn0 = 1;
+    p.mg_g0 = game_id_base;
+    p.mg_total = games_total;
+    p.mg_max_steps = max_steps;
+    p.mg_out_boards = (u64 *)out_boards;
+    p.mg_out_results = out_results;
+    p.mg_out_final = (u64 *)out_final;
+    p.mg_out_score = (long long *)out_score;
+    p.mg_out_steps = out_steps;
+    p.mg_out_status = out_status;
+    p.move_counter = (unsigned long long *)move_counter;
+    p.tb = tables_of(c);
+    p.err_flag = c->err_flag;
+    mg_init_kernel<<<LC(c, (unsigned)((G + 127) / 128)), 128, 0, st>>>(p, (const u64 *)starts, (long)G);
+    CK(cudaGetLastError());
     return launch_nn(c, precision, p, st);
 }
 

@@ -3,7 +3,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define N_COUNTERS 256
+#include <atomic>
+
+// Work cursors: every launch of a persistent kernel takes the next slot(s) of a rotating pool (atomic cursor, so
+// host threads and streams may share a context).  A slot is reused after N_COUNTERS further launches; the CUDA
+// launch queue is far shallower than that, so a slot is never shared by two launches in flight.
+#define N_COUNTERS 4096
 
 struct b2048_ctx {
     int device;
@@ -12,13 +17,11 @@ struct b2048_ctx {
     uint32_t *score;
     uint8_t *moved_fwd, *moved_rev, *legal;
     uint2 *rowstat;
-    int k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide
+    std::atomic<int> k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide
     unsigned long long *counters;  // N_COUNTERS work cursors, one per in-flight launch
-    int *err_flag;
-    unsigned next_counter;
-    // root-search scratch (grown on demand outside of stream capture; see b2048_mcts_fixed)
-    uint64_t *rboard;
-    int64_t rboard_cap;
+    int *err_flag;                 // [0] spawn on a full board (ValueError in the reference), [1] table self-check
+    std::atomic<unsigned> next_counter;
+    std::atomic<unsigned long long> launches;  // kernels launched through this context (b2048_launch_count)
 };
 
 // record the message returned by b2048_last_error(); return the status code of the failing entry point
@@ -30,3 +33,40 @@ int b2048_fail_msg(const char *what);
         cudaError_t e_ = (call);                       \
         if (e_ != cudaSuccess) return b2048_fail(#call, e_); \
     } while (0)
+
+// Every entry point runs with the context's device current and restores the caller's device on return, so a
+// context of GPU 1 can be used from a thread whose current device is GPU 0 (b2048_create used to leave
+// the device switched and no other call set it).
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int device) : prev(-1) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+            prev = cur;
+            cudaSetDevice(device);
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// `count` consecutive work cursors out of the rotating pool (count <= N_COUNTERS)
+static inline unsigned long long *take_counters(b2048_ctx *c, unsigned count) {
+    for (;;) {
+        unsigned cur = c->next_counter.load(std::memory_order_relaxed);
+        unsigned slot = cur % N_COUNTERS;
+        unsigned skip = (slot + count > N_COUNTERS) ? (N_COUNTERS - slot) : 0;  // do not wrap inside one launch
+        if (c->next_counter.compare_exchange_weak(cur, cur + skip + count, std::memory_order_relaxed))
+            return c->counters + ((slot + skip) % N_COUNTERS);
+    }
+}
+
+// launch accounting: every kernel launch of the library is written kernel<<<LC(c, grid), ...>>>
+template <typename G>
+static inline G LC(b2048_ctx *c, G grid) {
+    c->launches.fetch_add(1, std::memory_order_relaxed);
+    return grid;
+}

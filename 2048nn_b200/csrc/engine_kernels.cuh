@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(256) game_summary_kernel(const u64 *__restrict
     }
 }
 
-// root moves of G origins: legal flag, merge score and the moved board (mcts.py:21)
+// root moves of G origins: legal flag and merge score (mcts.py:21); the lines recompute the moved board themselves
 __global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, long G, uint8_t *__restrict__ legal,
-                                  u32 *__restrict__ rscore, u64 *__restrict__ rboard) {
+                                  u32 *__restrict__ rscore) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G * 4) return;
     u64 x = origins[i >> 2];
@@ -248,7 +248,6 @@ __global__ void root_moves_kernel(Tables tb, const u64 *__restrict__ origins, lo
     u64 f = move_exact(x, (int)(i & 3), tb, s);
     legal[i] = f != x;
     rscore[i] = s;
-    rboard[i] = f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -267,7 +266,7 @@ struct PlayParams {
     // work definition
     long n;                 // number of games (work items)
     const u64 *start;       // FRESH/START mode: start boards (NULL or 0 entry -> fresh board)
-    const u64 *rboard;      // ROOT mode: [G*4] boards after the root move
+    const u64 *origins;     // ROOT mode: [G] root boards (line r = 4*g + i starts from move(origins[g], i))
     const uint8_t *rlegal;  // ROOT mode: [G*4]
     const u32 *rscore;      // ROOT mode: [G*4]
     int root_mode;
@@ -379,7 +378,8 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel(const PlayParams
                     skip = true;
                 } else {
                     key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
-                    u64 rb = p.rboard[r];
+                    u32 rs_;
+                            u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs_);  // mcts.py:21
                     rs = p.rscore[r];
                     if (countzero(rb) == 0) {
                         *p.err_flag = 1;
@@ -540,7 +540,8 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
                             skip = true;
                         } else {
                             key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
-                            u64 rb = p.rboard[r];
+                            u32 rs_;
+                            u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs_);  // mcts.py:21
                             rs = p.rscore[r];
                             if (countzero(rb) == 0) {
                                 *p.err_flag = 1;

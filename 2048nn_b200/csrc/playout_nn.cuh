@@ -17,6 +17,32 @@
 
 namespace b2048 {
 
+// ---- device-resident main games -------------------------------------------------------------------------
+// One MainGame per main game of the launch, in caller-provided workspace (HBM, read/written through L2 only).
+// A main step = root moves of `board`, `number` policy lines per legal root move (work items in the MainQueue ring),
+// min accepted moves per root move (gmin, shared with the lines' early stop), then the line that retires last
+// ("closer": pending hits 0) picks argmax(1 + gmin), moves, spawns, records and queues the next step's lines.
+// Main games advance independently: no grid-wide step barrier, a free slot takes the next queued line of ANY game.
+struct MainGame {
+    u64 board;       // current main board
+    u64 key;         // main stream (seed, game id): start board and main spawns
+    long long score; // merge score of the main moves made
+    u64 rboard[4];   // boards after the four root moves of the current step
+    u32 rscore[4];
+    int step;        // main moves made
+    int pending;     // lines of the current root evaluation queued or running
+    int legal;       // bit i: root move i moves
+    int over;
+    int pad[10];
+};
+static_assert(sizeof(MainGame) == 128, "MainGame layout");
+struct MainQueue {
+    unsigned long long head, tail;  // consumed / produced line counts (ring index = count & (cap-1))
+    int games_alive;
+    int pad[11];
+};
+static_assert(sizeof(MainQueue) == 64, "MainQueue layout");
+
 struct NNPlayParams {
     Tables tb;
     const void *blob;   // folded weights: fp32 image (convnet_fp32.cuh) or fp16 tensor-core image (convnet_tc.cuh)
@@ -25,7 +51,7 @@ struct NNPlayParams {
     const u64 *start;  // start boards (NULL / 0 entry -> fresh board)
     // root mode
     int root_mode;
-    const u64 *rboard;      // [G*4] boards after the root move
+    const u64 *origins;     // [G] root boards; root move r = 4*g + i is recomputed by the line that starts from it
     const uint8_t *rlegal;  // [G*4]
     int number, line_begin, line_count;
     u64 seed, gid_base;
@@ -47,14 +73,29 @@ struct NNPlayParams {
     long blob_stride;      // bytes between consecutive models' weight images
     u64 gid_model_stride;  // game id offset per model (0: every model sees the same spawn streams)
     int *err_flag;
+    // device-resident main games (selfplay.py:62-115 with mcts_nn.py:4-43 as the search): see MainGame below
+    int main_mode;
+    MainGame *mg;               // [G] main-game states
+    MainQueue *mgq;             // line queue header
+    u32 *mg_items;              // ring of queued lines, mg_cap entries (power of two), 0 = empty
+    u32 mg_cap;
+    u64 mg_g0, mg_total;        // first main-game id of this launch, games of the whole session (eval-id stride)
+    int mg_max_steps;
+    u64 *mg_out_boards;         // [G][max_steps] board before each main move (may be NULL)
+    float *mg_out_results;      // [G][max_steps][4] root values the move was chosen from (may be NULL)
+    u64 *mg_out_final;          // [G]
+    long long *mg_out_score;    // [G]
+    int *mg_out_steps;          // [G] main moves made
+    int *mg_out_status;         // [G] 0 game over, 1 stopped at max_steps
 };
 
 struct GameSlot {
     u64 board, key;
     u32 score, count;
-    long slot;   // output index
+    long slot;   // output index (main mode: local main-game index)
     int group;   // -1 = none
     int live;
+    int closing; // main mode: this line was the last one of its main game's step -> its lane advances the game
 };
 
 // fetch + initialise one work item into `g`; returns false when the queue is empty.
@@ -66,6 +107,7 @@ __device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
         g.score = 0;
         g.count = 0;
         g.group = -1;
+        g.closing = 0;
         if (p.root_mode) {
             long r = item / p.line_count;
             int j = p.line_begin + (int)(item - r * p.line_count);
@@ -77,7 +119,8 @@ __device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
                 continue;
             }
             g.key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
-            u64 rb = p.rboard[r];
+            u32 rs;
+            u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs);  // mcts_nn.py:19
             if (countzero(rb) == 0) {
                 *p.err_flag = 1;
                 continue;
@@ -98,11 +141,18 @@ __device__ __forceinline__ bool nn_fetch(const NNPlayParams &p, GameSlot &g) {
 }
 
 __device__ __forceinline__ void nn_finish(const NNPlayParams &p, GameSlot &g) {
+    g.live = 0;
+    if (p.main_mode) {
+        // the group's minimum must be visible before this line is counted as retired (the closer reads it)
+        atomicMin(p.group_min + g.group, (int)g.count);
+        __threadfence();
+        g.closing = atomicSub(&p.mg[g.slot].pending, 1) == 1;
+        return;
+    }
     if (p.out_final) p.out_final[g.slot] = g.board;
     if (p.out_score) p.out_score[g.slot] = g.score;
     if (p.out_moves) p.out_moves[g.slot] = g.count;
     if (g.group >= 0) atomicMin(p.group_min + g.group, (int)g.count);
-    g.live = 0;
 }
 
 // One policy move for a live game given its 4 logits: directions in descending logit order
@@ -193,6 +243,216 @@ __device__ __forceinline__ void nn_move_cand(const NNPlayParams &p, GameSlot &g,
     moves_done++;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident main games: queue + main-move logic.  Everything below reads and writes the workspace with
+// volatile / atomic accesses (L2): the states are handed between SMs many times per launch.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T ld_vol(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+template <typename T>
+__device__ __forceinline__ void st_vol(T *p, T v) { *reinterpret_cast<volatile T *>(p) = v; }
+
+__device__ __forceinline__ void mg_finalize(const NNPlayParams &p, long gl, u64 board, long long score, int step, int status) {
+    p.mg_out_final[gl] = board;
+    p.mg_out_score[gl] = score;
+    p.mg_out_steps[gl] = step;
+    p.mg_out_status[gl] = status;
+    st_vol(&p.mg[gl].over, 1);
+    __threadfence();
+    atomicSub(&p.mgq->games_alive, 1);
+}
+
+// Root moves of the game's current board (mcts_nn.py:18-19): fills rboard / rscore / legal, resets the four minima
+// and `pending`.  Returns the legal mask; 0 = no root move moves -> mcts_nn returns [0,0,0,0], argmax is move 0, it
+// does not move: the main game is over (selfplay.py:95-98) and has been finalized here.
+__device__ __forceinline__ int mg_publish(const NNPlayParams &p, long gl, u64 board, long long score, int step) {
+    MainGame *s = p.mg + gl;
+    int mask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 sc;
+        const u64 f = move_exact(board, i, p.tb, sc);
+        if (f != board) {
+            if (countzero(f) == 0) {  // generate_tile on an emptied board: ValueError in the reference (board.py:87)
+                *p.err_flag = 1;
+                mask = 0;
+                break;
+            }
+            mask |= 1 << i;
+        }
+        st_vol(&s->rboard[i], f);
+        st_vol(&s->rscore[i], sc);
+        st_vol(p.group_min + gl * 4 + i, 0x7fffffff);
+    }
+    if (!mask) {
+        mg_finalize(p, gl, board, score, step, 0);
+        return 0;
+    }
+    st_vol(&s->legal, mask);
+    st_vol(&s->pending, __popc(mask) * p.number);
+    return mask;
+}
+
+// The closer's part of a main step (selfplay.py:93-105): values 1 + min (0 where illegal), first maximum, move,
+// spawn number `step` of the main stream, record.  Returns the next step's legal mask (0: the game has ended).
+__device__ __forceinline__ int mg_advance(const NNPlayParams &p, long gl) {
+    MainGame *s = p.mg + gl;
+    __threadfence();  // the retired lines' minima (released before their `pending` decrement)
+    const int legal = ld_vol(&s->legal);
+    const int step = ld_vol(&s->step);
+    const u64 board = ld_vol(&s->board);
+    float val[4];
+    int best = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        val[i] = ((legal >> i) & 1) ? (float)(ld_vol(p.group_min + gl * 4 + i) + 1) : 0.f;
+        if (val[i] > val[best]) best = i;  // np.argmax: first maximum
+    }
+    if (p.mg_out_boards) p.mg_out_boards[gl * p.mg_max_steps + step] = board;
+    if (p.mg_out_results)
+        reinterpret_cast<float4 *>(p.mg_out_results)[gl * p.mg_max_steps + step] = make_float4(val[0], val[1], val[2], val[3]);
+    const long long score = ld_vol(&s->score) + (long long)ld_vol(&s->rscore[best]);
+    u32 four;
+    const u64 nb = spawn_tile(ld_vol(&s->rboard[best]), rng_draw(ld_vol(&s->key), B2048_INIT_DRAWS + (u64)step), four);
+    st_vol(&s->board, nb);
+    st_vol(&s->score, score);
+    st_vol(&s->step, step + 1);
+    if (step + 1 >= p.mg_max_steps) {
+        mg_finalize(p, gl, nb, score, step + 1, 1);
+        return 0;
+    }
+    return mg_publish(p, gl, nb, score, step + 1);
+}
+
+// Queue the lines of game gl's current step: `number` per legal root move, ring slots [base, base + n).
+// Called by `nlanes` cooperating lanes (lane = 0..nlanes-1) after the game's state was written by one of them.
+__device__ __forceinline__ void mg_push(const NNPlayParams &p, long gl, int mask, unsigned long long base, int lane, int nlanes) {
+    const int n = __popc(mask) * p.number;
+    __threadfence();  // state before items
+    for (int k = lane; k < n; k += nlanes) {
+        int ii = k / p.number;
+        const int j = k - ii * p.number;
+        int i = 0;
+        for (int m = mask;; i++, m >>= 1)
+            if (m & 1) {
+                if (ii == 0) break;
+                ii--;
+            }
+        const u32 code = (u32)(gl * 4 * p.number + i * p.number + j) + 1u;
+        st_vol(p.mg_items + ((base + (unsigned long long)k) & (unsigned long long)(p.mg_cap - 1)), code);
+    }
+}
+
+// Start the queued line `code - 1` in slot g.
+__device__ __forceinline__ void mg_start_line(const NNPlayParams &p, GameSlot &g, u32 code) {
+    code -= 1u;
+    const u32 per = 4u * (u32)p.number;
+    const long gl = code / per;
+    const u32 rem = code - (u32)gl * per;
+    const int i = (int)(rem / (u32)p.number), j = (int)(rem - (u32)i * (u32)p.number);
+    const MainGame *s = p.mg + gl;
+    const u64 eval_id = ((u64)ld_vol(&s->step) + 1ULL) * p.mg_total + p.mg_g0 + (u64)gl;
+    g.key = rng_key(p.seed, (eval_id * 4ULL + (u64)i) * (u64)p.number + (u64)j);
+    u32 four;
+    g.board = spawn_tile(ld_vol(&s->rboard[i]), rng_draw(g.key, B2048_INIT_DRAWS), four);  // mcts_nn.py:22
+    g.score = 0;
+    g.count = 0;
+    g.slot = gl;
+    g.group = (int)gl * 4 + i;
+    g.closing = 0;
+    g.live = 1;
+}
+
+// Warp-level service routine of the main-game mode, called by all 32 lanes of a slot-owning warp after the move
+// phase: (1) lanes whose line closed a main step advance that game and queue its next lines (one closer at a time,
+// the warp writes the items together), (2) free slots claim queued lines (one CAS per warp), (3) a warp with nothing
+// live waits while main games are still running elsewhere.  `has_slot`: this lane owns a game slot.
+__device__ __noinline__ void mg_service(const NNPlayParams &p, GameSlot &g, bool has_slot, bool &queue_empty, int lane) {
+    MainQueue *q = p.mgq;
+    for (;;) {
+        unsigned cm = __ballot_sync(0xffffffffu, has_slot && g.closing);
+        while (cm) {
+            const int l = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const long gl = __shfl_sync(0xffffffffu, g.slot, l);
+            int mask = 0;
+            unsigned long long base = 0;
+            if (lane == l) {
+                mask = mg_advance(p, gl);
+                if (mask) base = atomicAdd(&q->tail, (unsigned long long)(__popc(mask) * p.number));
+                g.closing = 0;
+            }
+            mask = __shfl_sync(0xffffffffu, mask, l);
+            base = __shfl_sync(0xffffffffu, base, l);
+            __syncwarp();
+            if (mask) mg_push(p, gl, mask, base, lane, 32);
+        }
+        const bool want = has_slot && !g.live && !queue_empty;
+        const unsigned need = __ballot_sync(0xffffffffu, want);
+        if (need) {
+            int take = 0;
+            unsigned long long base = 0;
+            bool all_over = false;
+            if (lane == 0) {
+                const int cnt = __popc(need);
+                for (;;) {
+                    const unsigned long long h = ld_vol(&q->head);
+                    const long long avail = (long long)(ld_vol(&q->tail) - h);
+                    if (avail <= 0) {
+                        all_over = ld_vol(&q->games_alive) <= 0;
+                        break;
+                    }
+                    take = avail < cnt ? (int)avail : cnt;
+                    if (atomicCAS(&q->head, h, h + (unsigned long long)take) == h) {
+                        base = h;
+                        break;
+                    }
+                    take = 0;
+                }
+            }
+            take = __shfl_sync(0xffffffffu, take, 0);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            all_over = __shfl_sync(0xffffffffu, (int)all_over, 0) != 0;
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            if (want && rank < take) {
+                u32 *slot = p.mg_items + ((base + (unsigned long long)rank) & (unsigned long long)(p.mg_cap - 1));
+                u32 code;
+                while ((code = atomicExch(slot, 0u)) == 0u) __nanosleep(64);  // reserved by a producer, being written
+                __threadfence();
+                mg_start_line(p, g, code);
+            }
+            if (all_over && want) queue_empty = true;  // every main game has ended: nothing will be queued again
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, has_slot && g.live);
+        const unsigned open = __ballot_sync(0xffffffffu, has_slot && !queue_empty);
+        if (live || !open) return;
+        __nanosleep(512);  // all slots free, main games still running on other SMs: poll the queue
+    }
+}
+
+// One thread per main game: main stream key, start board, first root evaluation queued.
+__global__ void mg_init_kernel(const NNPlayParams p, const u64 *starts, long G) {
+    const long gl = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= G) return;
+    MainGame *s = p.mg + gl;
+    const u64 key = rng_key(p.seed, p.mg_g0 + (u64)gl);
+    const u64 s0 = starts ? starts[gl] : 0ULL;
+    const u64 board = s0 ? s0 : init_board(key);  // selfplay.py:83 `if not board`
+    s->key = key;
+    s->board = board;
+    s->score = 0;
+    s->step = 0;
+    s->over = 0;
+    atomicAdd(&p.mgq->games_alive, 1);
+    int mask = p.mg_max_steps > 0 ? mg_publish(p, gl, board, 0, 0) : 0;
+    if (p.mg_max_steps <= 0) mg_finalize(p, gl, board, 0, 0, 1);
+    if (mask) {
+        const unsigned long long base = atomicAdd(&p.mgq->tail, (unsigned long long)(__popc(mask) * p.number));
+        mg_push(p, gl, mask, base, 0, 1);
+    }
+}
+
 // Exact-mode kernel: 8 game slots per CTA, fp32 CUDA-core forward.
 __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -201,6 +461,8 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
     __shared__ int s_live;
     GameSlot g;
     g.live = 0;
+    g.closing = 0;
+    g.slot = 0;
     g.board = 0;
     u32 moves_done = 0;
     bool queue_empty = false;
@@ -210,8 +472,12 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
     for (;;) {
         if (t == 0) s_live = 0;
         __syncthreads();
-        if (t < CN_BOARDS_PER_CTA) {
+        if (p.main_mode) {
+            if (t < 32) mg_service(p, g, t < CN_BOARDS_PER_CTA, queue_empty, t);
+        } else if (t < CN_BOARDS_PER_CTA) {
             if (!g.live && !queue_empty) queue_empty = !nn_fetch(p, g);
+        }
+        if (t < CN_BOARDS_PER_CTA) {
             s_boards[t] = g.live ? g.board : 0ULL;
             if (g.live) atomicOr(&s_live, 1);
         }
@@ -228,7 +494,10 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
 // of each worker group's owner warp: consume the forward's logits (move choice, spawn, death), refill
 // from the global work counter, hand the next 32 boards to the network.  The engine phase of one set
 // overlaps the other set's forward.
-struct PlayWork {
+// MAIN = true: the device-resident main-game mode (slots are fed by the line queue, mg_service), a separate kernel
+// instantiation so that the plain playout kernel carries none of its code.
+template <bool MAIN>
+struct PlayWorkT {
     typedef NNPlayParams Params;
     struct State {
         GameSlot g;
@@ -240,6 +509,8 @@ struct PlayWork {
     }
     __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
+        st.g.closing = 0;
+        st.g.slot = 0;
         st.g.board = 0;
         st.moves_done = 0;
         // latency mode (few work items): one tile-set per CTA so a step is not interleaved with a second set
@@ -274,7 +545,8 @@ struct PlayWork {
         dbg_base = 0;
         if (!first && st.g.live)
             nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
-        if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
+        if (MAIN) mg_service(p, st.g, true, st.queue_empty, lane);
+        else if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
         s_boards[lane] = st.g.live ? st.g.board : 0ULL;
         const unsigned any = __ballot_sync(0xffffffffu, st.g.live);
         if (!any && p.move_counter) {
@@ -285,5 +557,7 @@ struct PlayWork {
         return any != 0;
     }
 };
+typedef PlayWorkT<false> PlayWork;
+typedef PlayWorkT<true> MainWork;
 
 }  // namespace b2048

@@ -101,7 +101,10 @@ def _sharded(run, origins, number, eval_id_base, group):
     G = origins.numel()
     o0, o1, l0, l1 = shard_plan(G, number, rank, ws)
     if ws > 1 and (o0, o1, l0, l1) == (0, G, 0, int(number)):
-        return run(origins, eval_id_base, 0, int(number))  # replicated: identical on every rank, no exchange
+        r = run(origins, eval_id_base, 0, int(number))  # replicated: identical on every rank, no exchange
+        if rank and r.get("total_moves") is not None:
+            r["total_moves"].zero_()  # count the replicated work once
+        return r
     if (o0, o1) == (0, G):
         r = run(origins, eval_id_base, l0, l1)
     else:
@@ -111,9 +114,16 @@ def _sharded(run, origins, number, eval_id_base, group):
         if part.get("total_moves") is not None:
             r["total_moves"] = part["total_moves"]
     allreduce_root_stats(r, group)
-    if ws > 1 and r.get("total_moves") is not None:
-        dist.all_reduce(r["total_moves"], op=dist.ReduceOp.SUM, group=group)
+    # r["total_moves"] (throughput accounting) stays THIS RANK's count: callers sum it over ranks once, at the end of
+    # a run, instead of paying a second collective per root evaluation (sum_over_ranks below)
     return r
+
+
+def sum_over_ranks(t, group=None):
+    """In-place SUM allreduce of an accounting tensor (no-op without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 def mcts_fixed_sharded(origins, number, seed, eval_id_base=0, group=None):

@@ -318,3 +318,29 @@ def selfplay_fixed_games(G, number, seed, times=1, mode=2, starts=None, game_id_
         L.ptr(r["results"]), L.ptr(r["final"]), L.ptr(r["score"]), L.ptr(r["steps"]), L.ptr(r["status"]),
         L.ptr(r["total_moves"]), L.stream_ptr(d)))
     return r
+
+
+def selfplay_nn_games(blob, precision, G, number, seed, starts=None, game_id_base=0, games_total=None, max_steps=4096,
+                      record=True, device="cuda"):
+    """Whole NN-policy root-search main games on the device (b2048_selfplay_nn; selfplay.py:62-115 with mcts_nn as the
+    search): one persistent launch, lines of all main games flow through a device-side queue, no per-step barrier.
+    -> dict(boards i64[G,max_steps], results f32[G,max_steps,4] (record=True), final i64[G], score i64[G], steps i32[G],
+            status i32[G] (1 = stopped at max_steps), total_moves i64[1])"""
+    L.require_cuda()
+    d = torch.device(device) if starts is None else _dev(starts)
+    games_total = game_id_base + G if games_total is None else games_total
+    lib = L.load_library()
+    wbytes = lib.b2048_selfplay_nn_workspace_bytes(G, int(number))
+    if wbytes < 0:
+        raise ValueError("G * 4 * number is too large for one launch")
+    work = torch.empty(wbytes, dtype=torch.uint8, device=d)  # torch's allocator returns 512-byte aligned blocks
+    r = dict(boards=torch.empty((G, max_steps), dtype=torch.int64, device=d) if record else None,
+             results=torch.empty((G, max_steps, 4), dtype=torch.float32, device=d) if record else None,
+             final=torch.empty(G, dtype=torch.int64, device=d), score=torch.empty(G, dtype=torch.int64, device=d),
+             steps=torch.empty(G, dtype=torch.int32, device=d), status=torch.empty(G, dtype=torch.int32, device=d),
+             total_moves=torch.zeros(1, dtype=torch.int64, device=d), workspace=work)
+    L.check(lib.b2048_selfplay_nn(
+        L.ctx(d), PRECISIONS[precision], L.ptr(blob), L.ptr(starts), G, game_id_base, games_total, int(number), seed,
+        int(max_steps), L.ptr(r["boards"]), L.ptr(r["results"]), L.ptr(r["final"]), L.ptr(r["score"]), L.ptr(r["steps"]),
+        L.ptr(r["status"]), L.ptr(r["total_moves"]), L.ptr(work), L.stream_ptr(d)))
+    return r

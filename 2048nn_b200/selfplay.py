@@ -2,10 +2,13 @@
 
 `selfplay` / `selfplay_fixed` keep the reference's single-game signatures and npz format
 (selfplay.py:55-58,111-114: boards uint64[T], results float32[T,4], score).  `selfplay_batch`
-is the B200 shape of BASELINE config 4: G main games advance in lock-step; every main step is
-ONE persistent-kernel launch evaluating G x 4 x number playout lines (sharded over the process
-group's GPUs), one [G,4] allreduce, and a handful of tiny device ops to pick argmax, move and
-spawn.  The main boards stay on the device; the host reads one scalar per main step."""
+is the B200 shape of BASELINE config 4: G main games played DEVICE-RESIDENT -- fixed-order search:
+one CTA per main game (b2048_selfplay_fixed); NN-policy search: one persistent tensor-core launch whose
+game slots are fed by a device-side queue of root-evaluation lines (b2048_selfplay_nn), so main games advance
+independently with no host round trip and no barrier per main move.  Main games are sharded over the process
+group's GPUs by game id; the only collectives are the final gather of the records and the move-count sum.
+`_selfplay_batch_steps` is the lock-step host loop (one root-evaluation launch + [G,4] allreduce per main step,
+lines or origins sharded by dist.shard_plan) that the device-resident paths are tested against."""
 import os
 
 import numpy as np
@@ -23,22 +26,41 @@ def _eval_ids(step, G):
 
 
 def selfplay_batch(G, number=10, model=None, times=1, seed=None, precision=None, starts=None, max_steps=100000,
-                   group=None):
+                   group=None, game_id_base=0, games_total=None, lockstep=False):
     """Play G main games to the end.  model=None -> fixed-order playouts scored by
     mcts_fixed_min averaged over `times` (selfplay.py:9-59); else NN-policy mcts_nn (selfplay.py:62-115).
 
-    Returns a list of G records dict(boards uint64[T], results float32[T,4], score int) and the
-    total number of playout moves (all ranks).
+    Returns a list of G records dict(boards uint64[T], results float32[T,4], score int, truncated bool) and the
+    total number of playout moves (all ranks).  `truncated` marks a game that was still running after max_steps
+    main moves (its record is a prefix and must not be saved as a finished game).
 
-    Fixed-order games run device-resident (one CTA per main game, b2048_selfplay_fixed), main games sharded over the
-    process group; NN-policy games advance in lock-step with lines sharded (`_selfplay_batch_steps`).  Both give the
-    same games for every world size."""
-    if model is None and times <= 64:
-        return _selfplay_fixed_device(G, number, times, _session_seed(seed), starts, max_steps, group)
-    return _selfplay_batch_steps(G, number, model, times, seed, precision, starts, max_steps, group)
+    Main game k of the call is game id game_id_base + k of a session of games_total games (default: this call's G):
+    the same (seed, game id, games_total) always gives the same game, whatever the batch it is played in and however
+    the batch is sharded over GPUs.  lockstep=True forces the step-by-step host loop."""
+    s = _session_seed(seed)
+    if lockstep or (model is None and times > 64):
+        if game_id_base or games_total not in (None, G):
+            raise ValueError("the lock-step loop plays whole sessions (game_id_base = 0, games_total = G)")
+        return _selfplay_batch_steps(G, number, model, times, seed, precision, starts, max_steps, group)
+    gt = game_id_base + G if games_total is None else int(games_total)
+    if model is None:
+        def launch(n_local, g0, st, budget):
+            return engine.selfplay_fixed_games(n_local, int(number), s, times=int(times), mode=2, starts=st,
+                                               game_id_base=game_id_base + g0, games_total=gt, max_steps=budget)
+        first_budget = 4096
+    else:
+        blob, prec = blob_for(model, precision)
+
+        def launch(n_local, g0, st, budget):
+            return engine.selfplay_nn_games(blob, prec, n_local, int(number), s, starts=st, game_id_base=game_id_base + g0,
+                                            games_total=gt, max_steps=budget)
+        first_budget = 16384  # a strong policy's main games run to several thousand moves; a replay costs minutes
+    return _device_games(launch, G, starts, max_steps, first_budget, group)
 
 
-def _selfplay_fixed_device(G, number, times, s, starts, max_steps, group):
+def _device_games(launch, G, starts, max_steps, first_budget, group):
+    """Shard G device-resident main games over the process group, replay with a larger step budget while some
+    game outlives it, gather every rank's records."""
     import torch.distributed as td
     dev = torch.device("cuda")
     world = td.get_world_size(group) if td.is_available() and td.is_initialized() else 1
@@ -46,13 +68,12 @@ def _selfplay_fixed_device(G, number, times, s, starts, max_steps, group):
     per = (G + world - 1) // world
     g0 = min(G, rank * per)
     n_local = max(0, min(G, g0 + per) - g0)
-    budget = int(min(max_steps, 4096))
+    budget = int(min(max_steps, first_budget))
     while True:
         r = None
         if n_local:
             st = None if starts is None else starts.to(dev)[g0:g0 + n_local].contiguous()
-            r = engine.selfplay_fixed_games(n_local, int(number), s, times=int(times), mode=2, starts=st, game_id_base=g0,
-                                            games_total=G, max_steps=budget)
+            r = launch(n_local, g0, st, budget)
         _raise_if_flag()
         clipped = torch.zeros(1, dtype=torch.int32, device=dev)
         if r is not None:
@@ -70,6 +91,7 @@ def _selfplay_fixed_device(G, number, times, s, starts, max_steps, group):
         return out
     steps = padded(r["steps"] if r else None, (), torch.int32)
     score = padded(r["score"] if r else None, (), torch.int64)
+    status = padded(r["status"] if r else None, (), torch.int32)
     boards = padded(r["boards"] if r else None, (budget,), torch.int64)
     results = padded(r["results"] if r else None, (budget, 4), torch.float32)
     moves = r["total_moves"].clone() if r else torch.zeros(1, dtype=torch.int64, device=dev)
@@ -78,11 +100,12 @@ def _selfplay_fixed_device(G, number, times, s, starts, max_steps, group):
             out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
             td.all_gather_into_tensor(out, t.contiguous(), group=group)
             return out.reshape((world * per,) + tuple(t.shape[1:]))
-        steps, score, boards, results = gather(steps), gather(score), gather(boards), gather(results)
+        steps, score, status, boards, results = gather(steps), gather(score), gather(status), gather(boards), gather(results)
         td.all_reduce(moves, group=group)
-    hs, hsc = steps.cpu().numpy(), score.cpu().numpy()
+    hs, hsc, hst = steps.cpu().numpy(), score.cpu().numpy(), status.cpu().numpy()
     hb, hr = boards.cpu().numpy().view(np.uint64), results.cpu().numpy()
-    records = [dict(boards=hb[g, :hs[g]].copy(), results=hr[g, :hs[g]].copy(), score=int(hsc[g])) for g in range(G)]
+    records = [dict(boards=hb[g, :hs[g]].copy(), results=hr[g, :hs[g]].copy(), score=int(hsc[g]), truncated=bool(hst[g]))
+               for g in range(G)]
     return records, int(moves.item())
 
 
@@ -128,6 +151,7 @@ def _selfplay_batch_steps(G, number=10, model=None, times=1, seed=None, precisio
         step += 1
         if not bool(alive.any().item()):  # the one host read per main step
             break
+    _dist.sum_over_ranks(total_moves, group)
     hb = torch.stack(hist_b).cpu().numpy().view(np.uint64)  # [T, G]
     hr = torch.stack(hist_r).cpu().numpy()
     ha = torch.stack(hist_alive).cpu().numpy()
@@ -135,81 +159,85 @@ def _selfplay_batch_steps(G, number=10, model=None, times=1, seed=None, precisio
     records = []
     for g in range(G):
         T = int(ha[:, g].sum())  # steps are contiguous from 0 while the game advances
-        records.append(dict(boards=hb[:T, g].copy(), results=hr[:T, g].copy(), score=int(sc[g])))
+        records.append(dict(boards=hb[:T, g].copy(), results=hr[:T, g].copy(), score=int(sc[g]),
+                            truncated=bool(step >= max_steps and ha[-1, g])))
     return records, int(total_moves.item())
 
 
 def save_record(path, rec):
-    """selfplay.py:55-58 / 111-114 npz format."""
+    """selfplay.py:55-58 / 111-114 npz format.  A record cut off by the step budget is not a finished game."""
+    if rec.get("truncated"):
+        raise ValueError("refusing to save a truncated self-play record (raise max_steps)")
     np.savez(path, boards=np.asarray(rec["boards"], dtype=np.uint64), results=np.asarray(rec["results"], dtype=np.float32),
              score=rec["score"])
 
 
-def selfplay_fixed(name, board=None, number=10, times=1, verbose=False, seed=None, out_dir='selfplay/fixed10/'):
+CLI_SESSION_SEED = 2048       # command-line records: stream seed shared by every record ...
+CLI_GAMES_TOTAL = 1 << 32     # ... of one fixed session of 2^32 main games; --seed N selects main game N of it
+
+
+def selfplay_fixed(name, board=None, number=10, times=1, verbose=False, seed=None, out_dir='selfplay/fixed10/',
+                   game_id=0, games_total=None):
     """selfplay.py:9-59 (single main game, fixed-order min-move search)."""
     print(f'fixed {number} lines, {times} times')
     starts = None if not board else torch.from_numpy(np.array([board], np.uint64).view(np.int64))
-    recs, _ = selfplay_batch(1, number, None, times, seed, starts=starts)
-    rec = recs[0]
-    print('Score {}'.format(rec["score"]))
-    print('{} moves'.format(len(rec["boards"])))
-    os.makedirs(out_dir, exist_ok=True)
-    save_record(os.path.join(out_dir, name), rec)
-    print('Saved as {}.npz'.format(name))
-    return rec
+    recs, _ = selfplay_batch(1, number, None, times, seed, starts=starts, game_id_base=game_id, games_total=games_total)
+    return _report_and_save(recs[0], out_dir, name, 'Saved as {}.npz')
 
 
-def selfplay(name, model, board=None, number=10, device='cuda', verbose=False, seed=None, out_dir='selfplay/'):
+def selfplay(name, model, board=None, number=10, device='cuda', verbose=False, seed=None, out_dir='selfplay/',
+             game_id=0, games_total=None):
     """selfplay.py:62-115 (single main game, mcts_nn search)."""
     print('Seed {}'.format(name))
     starts = None if not board else torch.from_numpy(np.array([board], np.uint64).view(np.int64))
-    recs, _ = selfplay_batch(1, number, model, 1, seed, starts=starts)
-    rec = recs[0]
+    recs, _ = selfplay_batch(1, number, model, 1, seed, starts=starts, game_id_base=game_id, games_total=games_total)
+    return _report_and_save(recs[0], out_dir, name, 'Saved {}.npz')
+
+
+def _report_and_save(rec, out_dir, name, fmt):
     print('Score {}'.format(rec["score"]))
     print('{} moves'.format(len(rec["boards"])))
     os.makedirs(out_dir, exist_ok=True)
     save_record(os.path.join(out_dir, name), rec)
-    print('Saved {}.npz'.format(name))
+    print(fmt.format(name))
     return rec
 
 
 def main(argv=None):
-    """selfplay.py:118-152: `--seed N` plays main game N (fixed-order min-move search, number=10, times=4, as the
-    reference's default branch) and saves it as selfplay/fixed10/NNNNN.npz.  `--games K` generates K records
-    (seeds N..N+K-1) in one device-resident launch; `--model PATH` switches to the mcts_nn search of selfplay()."""
-    import random
+    """Command line of selfplay.py:118-152.  `--seed N` names the record NNNNN.npz as the reference does; here N is
+    the main-game id inside one fixed session (stream seed CLI_SESSION_SEED, CLI_GAMES_TOTAL games), so record N is
+    the same game whether it is produced alone (`--seed N`) or as part of a batch (`--seed M --games K`, records
+    M..M+K-1 in one device-resident launch).  Default search: fixed-order min-move, number=10, times=4
+    (the reference's default branch) -> selfplay/fixed10/; `--model PATH` -> mcts_nn search -> selfplay/."""
     from argparse import ArgumentParser
     from time import time
 
     parser = ArgumentParser()
-    parser.add_argument('--seed', type=int, default=12345, help='Number to use as seed and save name')
+    parser.add_argument('--seed', type=int, default=12345, help='main-game id = save name of the (first) record')
     parser.add_argument('--verbose', action='store_true', help='Verbose output')
-    parser.add_argument('--games', type=int, default=1, help='records to generate: seeds seed..seed+games-1')
+    parser.add_argument('--games', type=int, default=1, help='records to generate: main games seed..seed+games-1')
     parser.add_argument('--model', type=str, default='', help='c64b3 state_dict (.pt): NN-policy search instead of fixed-order')
     parser.add_argument('--number', type=int, default=10)
     args = parser.parse_args(argv)
     if args.seed < 0:
         raise ValueError('Seed is {}'.format(args.seed))
-    random.seed(args.seed)
-    np.random.seed(args.seed)
-    torch.manual_seed(args.seed)
     start_time = time()
+    model, out_dir, times = None, 'selfplay/fixed10/', 4
     if args.model:
         from .network import ConvNet
         model = ConvNet(channels=64, blocks=3, precision="fp16")
         model.load_state_dict(torch.load(args.model, map_location="cpu"))
         model.to('cuda').eval()
-        for k in range(args.games):
-            selfplay(str(args.seed + k).zfill(5), model, number=args.number, verbose=args.verbose, seed=args.seed + k)
-    elif args.games == 1:
-        selfplay_fixed(str(args.seed).zfill(5), number=args.number, times=4, verbose=args.verbose, seed=args.seed)
+        out_dir, times = 'selfplay/', 1
+        print(f'mcts_nn {args.number} lines, {args.games} games')
     else:
-        print(f'fixed {args.number} lines, 4 times, {args.games} games')
-        recs, _ = selfplay_batch(args.games, args.number, None, 4, seed=args.seed)
-        os.makedirs('selfplay/fixed10/', exist_ok=True)
-        for k, rec in enumerate(recs):
-            save_record(os.path.join('selfplay/fixed10/', str(args.seed + k).zfill(5)), rec)
-        print('Saved {} records, mean score {:.0f}'.format(len(recs), np.mean([r["score"] for r in recs])))
+        print(f'fixed {args.number} lines, {times} times, {args.games} games')
+    recs, _ = selfplay_batch(args.games, args.number, model, times, seed=CLI_SESSION_SEED, game_id_base=args.seed,
+                             games_total=CLI_GAMES_TOTAL)
+    os.makedirs(out_dir, exist_ok=True)
+    for k, rec in enumerate(recs):
+        save_record(os.path.join(out_dir, str(args.seed + k).zfill(5)), rec)
+        print('Saved {}.npz: score {}, {} moves'.format(str(args.seed + k).zfill(5), rec["score"], len(rec["boards"])))
     total_time = time() - start_time
     print(f'Took {total_time/60:.1f} minutes')
 

@@ -8,9 +8,14 @@
  * Conventions
  *   - every data pointer is a DEVICE pointer unless the name ends in _host;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is
- *     enqueued on it, nothing synchronises the host, nothing allocates after b2048_create
- *     (one exception: b2048_mcts_* grow a root-board scratch buffer when G exceeds every
- *     earlier call's G; b2048_take_error_flag is the one call that synchronises);
+ *     enqueued on it, nothing synchronises the host and nothing allocates after b2048_create
+ *     (b2048_take_error_flag is the one call that synchronises);
+ *   - a context belongs to one device; every call makes that device current for its own duration and restores
+ *     the caller's current device, so contexts of several GPUs can be driven from one thread;
+ *   - calls on one context may be issued from several host threads and on several streams concurrently: the
+ *     per-launch work cursors come from an atomic rotating pool and no launch shares scratch memory with another
+ *     (the error flag is per context: it says that SOME launch since the last b2048_take_error_flag hit the
+ *     reference's ValueError case);
  *   - return value: 0 = ok, non-zero = error (b2048_last_error() gives the text);
  *   - boards are uint64: nibble k (bits 4k..4k+3) is the tile exponent of cell
  *     (row k/4, col k%4), nibble 0 = top-left (board.py:23-33, 228-233);
@@ -57,6 +62,8 @@ const char *b2048_last_error(void);
 int b2048_create(int device, b2048_ctx **out);
 int b2048_destroy(b2048_ctx *ctx);
 int b2048_num_sms(const b2048_ctx *ctx);
+/* kernels launched through this context since b2048_create (launch accounting of bench.py's gpu_launches) */
+int64_t b2048_launch_count(const b2048_ctx *ctx);
 
 /* Fixed-order playout kernel variant: 1 (default) = legality-first with one uniform table slide per
  * move; 0 = the L,U,D,R attempt cascade.  Both are bit-exact; the switch exists for A/B measurements. */
@@ -233,6 +240,28 @@ int b2048_selfplay_fixed(b2048_ctx *ctx, const uint64_t *starts, int64_t G, uint
                          int number, int times, int mode, uint64_t seed, int max_steps, uint64_t *out_boards,
                          float *out_results, uint64_t *out_final, int64_t *out_score, int32_t *out_steps,
                          int32_t *out_status, uint64_t *move_counter, void *stream);
+
+/* Whole main games of the NN-policy root search on the device: selfplay() (selfplay.py:62-115) = per main move
+ * mcts_nn(model, board, number) (mcts_nn.py:4-43), np.argmax (first maximum), move, generate_tile, until the chosen
+ * move does not move.  One persistent launch plays G main games to the end (or to max_steps main moves) with NO
+ * host round trip and NO grid-wide barrier per main move: the lines of every root evaluation are work items of a
+ * device-side queue, a free game slot takes the next queued line of any main game, and the line that retires last
+ * advances its main game and queues the next evaluation.  Streams are those of the step-by-step host loop
+ * (b2048_mcts_nn + b2048_move_batch + b2048_spawn_batch), so the games are identical: main game
+ * m = game_id_base + g takes its start board / main spawns from stream (seed, m); the evaluation at main step s has
+ * eval_id = (s + 1)*games_total + m (line j of root move i: game (eval_id*4 + i)*number + j, first spawn k = 0).
+ *   workspace     device memory of b2048_selfplay_nn_workspace_bytes(G, number) bytes, 256-byte aligned (queue +
+ *                 game states; caller-allocated, nothing is allocated here)
+ *   out_boards    u64[G*max_steps] board before each main move, out_results f32[G*max_steps*4] = mcts_nn's list
+ *                 (1 + fewest moves survived; 0 illegal) it was chosen from -- the npz record of selfplay.py:111-114
+ *                 (each may be NULL)
+ *   out_final/out_score (i64)/out_steps [G]; out_status[G]: 0 game over, 1 stopped at max_steps
+ *   move_counter  optional u64[1], += policy moves played by the lines */
+int64_t b2048_selfplay_nn_workspace_bytes(int64_t G, int number);
+int b2048_selfplay_nn(b2048_ctx *ctx, int precision, const void *blob, const uint64_t *starts, int64_t G,
+                      uint64_t game_id_base, uint64_t games_total, int number, uint64_t seed, int max_steps,
+                      uint64_t *out_boards, float *out_results, uint64_t *out_final, int64_t *out_score,
+                      int32_t *out_steps, int32_t *out_status, uint64_t *move_counter, void *workspace, void *stream);
 
 /* ---- c64b3 training step (trainer.py:14-97) -------------------------------------------------
  * One optimisation step of trainer.py:55-62 -- m(x) in train mode (BatchNorm batch statistics, running-stat

@@ -285,3 +285,43 @@ def nn_games(sd, starts, keys, spawn0=0, stop_at_first_death=False, max_steps=1 
         if deaths and stop_at_first_death:
             break
     return boards, scores, moves, steps
+
+
+def mcts_nn(sd, origin, number=10, seed=0, eval_id=0, want_moves=False):
+    """mcts_nn.py:4-43 on per-line injected streams (line j of root move i of evaluation e is game
+    (e*4+i)*number+j, first spawn k = 0): 1 + the fewest policy moves any line survives, 0 for an illegal move.
+    want_moves: also return the number of accepted line moves played (the playout-moves metric)."""
+    out, played = [], 0
+    for i in range(4):
+        b, _, m = move(origin, i)
+        if not m:
+            out.append(0)
+            continue
+        keys = np.array([rng_key(seed, line_gid(eval_id, i, j, number)) for j in range(number)], np.uint64)
+        starts = np.array([spawn(b, int(k), 0) for k in keys], np.uint64)  # mcts_nn.py:22
+        _, _, mv, _ = nn_games(sd, starts, keys, spawn0=1, stop_at_first_death=True)
+        out.append(1 + int(mv.min()))
+        played += int(mv.sum())
+    return (out, played) if want_moves else out
+
+
+def selfplay_nn(sd, G, number, seed, max_steps, game_id_base=0, games_total=None):
+    """selfplay.py:62-115 for main games game_id_base..+G-1 of a session of games_total games, at most max_steps main
+    moves each: list of (boards u64[T], results f32[T,4], score, final board)."""
+    games_total = game_id_base + G if games_total is None else games_total
+    recs = []
+    for g in range(game_id_base, game_id_base + G):
+        key = rng_key(seed, g)
+        b, score, hb, hr = init_board(key), 0, [], []
+        for step in range(max_steps):
+            res = mcts_nn(sd, b, number, seed, (step + 1) * games_total + g)
+            i = int(np.argmax(res))           # selfplay.py:95
+            f, s, m = move(b, i)
+            if not m:                          # selfplay.py:96-98
+                break
+            hb.append(b)
+            hr.append(res)
+            b = spawn(f, key, step)
+            score += s
+        recs.append((np.array(hb, np.uint64), np.array(hr, np.float32).reshape(-1, 4), score, b))
+    return recs
