@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "playout moves/sec (fixed-order, play_fixed_batch to termination)"
+NN_METRIC = "playout moves/sec (c64b3 NN-policy, mcts_nn root evaluations)"
 UNIT = "moves/s"
 INSTR_PER_MOVE = 250.0  # algorithmic thread-instructions per accepted move
 
@@ -104,6 +105,39 @@ def cpu_port_rate(target_seconds, nthreads):
     return float(c.sum()) / dt, f"{n} fresh fixed-order games ({int(c.sum())} moves) in {dt:.2f}s wall"
 
 
+def shipped_state_dict():
+    """The c64b3 checkpoint of the reference (models/20200213, fixture copy) as a state dict, or None."""
+    import numpy as np
+    import torch
+
+    gpath = os.path.join(ROOT, "tests", "golden", "c64b3_golden.npz")
+    if not os.path.exists(gpath):
+        return None
+    ng = np.load(gpath)
+    return {k[len("sd_shipped/"):]: torch.from_numpy(np.array(ng[k])) for k in ng.files if k.startswith("sd_shipped/")}
+
+
+def cpu_nn_rate(target_seconds, nthreads):
+    """Oracle port of mcts_nn.mcts_nn(model, b, 50, 'cpu') (mcts_nn.py:4-43: torch fp32 ConvNet on `nthreads` intra-op
+    threads + the C board engine) on fresh boards -> (NN-policy moves/s, ms per call, sample str)."""
+    import torch
+    from oracle import oracle
+
+    oracle.lib()
+    torch.set_num_threads(nthreads)
+    sd = shipped_state_dict()
+    calls, moves, t0 = 0, 0, time.perf_counter()
+    while True:
+        b = oracle.init_board(oracle.rng_key(4242, calls))
+        _, mv = oracle.mcts_nn(sd, b, 50, 100, calls, want_moves=True)
+        calls += 1
+        moves += mv
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds or calls >= 8:
+            break
+    return moves / dt, dt / calls * 1e3, f"{calls} mcts_nn(number=50) call(s) from fresh boards, shipped c64b3, {moves} policy moves in {dt:.2f}s wall"
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -129,27 +163,145 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_nn:
+        nv, ms_call, nsample = cpu_nn_rate(args.cpu_seconds, cores)
+        line["nn_policy"] = {"metric": NN_METRIC, "value": nv, "unit": UNIT, "ms_per_mcts_nn_call": ms_call,
+                             "cpu_baseline": {"value": nv, "unit": UNIT, "cores": cores, "kind": "port", "sample": nsample}}
     print(json.dumps(line), flush=True)
 
 
+def torch_forward(m, x):
+    """The reference's ConvNet.forward (network.py:78-87) in plain PyTorch on the module tree of the drop-in
+    (cuDNN / cuBLAS kernels): the existing Blackwell implementation the hand-written forward has to beat."""
+    import torch
+
+    x = m.in_block(x)
+    for blk in m.blocks:
+        x = torch.relu(x + blk(x))
+    x = m.out_block(x)
+    return torch.log_softmax(m.policy(x.reshape(-1, m.out_size)), dim=1)
+
+
+def torch_forward_baselines(pkg, m, boards):
+    """Eager fp32 and channels_last + bf16-autocast forward of the same network on the same GPU, pre-encoded one-hot
+    input already resident (the encoder is not timed: favourable to the baseline)."""
+    import torch
+
+    n, chunk = boards.numel(), 1 << 17
+    out = {}
+    with torch.no_grad():
+        x = pkg.engine.encode_boards(boards[:chunk].contiguous())  # (chunk,16,4,4) fp32
+        for name in ("eager_fp32", "channels_last_bf16_autocast"):
+            if name == "eager_fp32":
+                xin, mod = x, m
+
+                def run():
+                    return torch_forward(mod, xin)
+            else:
+                xin, mod = x.contiguous(memory_format=torch.channels_last), m.to(memory_format=torch.channels_last)
+
+                def run():
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return torch_forward(mod, xin)
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(1, n // chunk)
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = reps * chunk / (e0.elapsed_time(e1) * 1e-3)
+    out["note"] = ("same module tree through cuDNN/cuBLAS, %d boards as %d launches-sets of %d pre-encoded one-hot boards "
+                   "(1,024 B/board resident in HBM; encoder not timed)" % (n, max(1, n // chunk), chunk))
+    return out
+
+
+def main_games_block(pkg, blob, G_total, number, main_steps, steps, warmup, seed0, rank, world, barrier):
+    """Device-resident NN main games (b2048_selfplay_nn): G_total main games of a session sharded over the ranks by
+    game id (strong scaling), each played for `main_steps` main moves per bench step.  Timed twice: device-resident
+    (start boards on the device, records left on the device) and end to end (pinned host start boards in, records
+    and results copied back to pinned host memory inside the timed region)."""
+    import torch
+
+    eng = pkg.engine
+    per = (G_total + world - 1) // world
+    g0 = min(G_total, rank * per)
+    n_local = max(0, min(G_total, g0 + per) - g0)
+    lc = pkg._lib.launch_count
+
+    def play(seed, starts=None):
+        if not n_local:
+            return None
+        return eng.selfplay_nn_games(blob, "fp16", n_local, number, seed, starts=starts, game_id_base=g0, games_total=G_total,
+                                     max_steps=main_steps)
+
+    for w in range(max(3, warmup)):
+        play(seed0 + w)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    moves = torch.zeros(1, dtype=torch.int64, device="cuda")
+    mains = torch.zeros(1, dtype=torch.int64, device="cuda")
+    l0 = lc()
+    e0.record()
+    for k in range(steps):
+        r = play(seed0 + 100 + k)
+        if r is not None:
+            moves += r["total_moves"]
+            mains += r["steps"].sum()
+    e1.record()
+    barrier()
+    launches = lc() - l0
+    # end to end: host start boards -> device, main games, records -> host
+    h2d = d2h = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_moves = 0
+    if n_local:
+        h_start = eng.init_boards(n_local, seed0 + 999, g0).cpu().pin_memory()
+        d_start = torch.empty(n_local, dtype=torch.int64, device="cuda")
+        hb = torch.empty((n_local, main_steps), dtype=torch.int64).pin_memory()
+        hr = torch.empty((n_local, main_steps, 4), dtype=torch.float32).pin_memory()
+        hs = torch.empty((3, n_local), dtype=torch.int64).pin_memory()
+        hm = torch.empty(1, dtype=torch.int64).pin_memory()
+        h2d = n_local * 8
+        d2h = hb.numel() * 8 + hr.numel() * 4 + hs.numel() * 8 + 8
+    barrier()
+    t0.record()
+    for k in range(steps):
+        if n_local:
+            d_start.copy_(h_start, non_blocking=True)
+            r = play(seed0 + 200 + k, starts=d_start)
+            hb.copy_(r["boards"], non_blocking=True)
+            hr.copy_(r["results"], non_blocking=True)
+            hs.copy_(torch.stack([r["final"], r["score"], r["steps"].to(torch.int64)]), non_blocking=True)
+            hm.copy_(r["total_moves"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            e2e_moves += int(hm[0]) + 0 * int(hs[1, 0])  # the step's results, read on the host
+    t1.record()
+    barrier()
+    return {"ms": e0.elapsed_time(e1), "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "mains": float(mains.item()),
+            "e2e_moves": float(e2e_moves), "launches": launches, "h2d": h2d, "d2h": d2h, "games_local": n_local}
+
+
 def nn_policy_block(pkg, args, rank, world, barrier):
-    """K steps of one sharded mcts_nn root evaluation: G origins x 4 root moves x `number` lines, lines
-    sharded over ranks, [G,4] min allreduce (NCCL) per step."""
+    """K steps of one sharded mcts_nn root evaluation: G origins x 4 root moves x `number` lines, sharded over the
+    ranks by dist.shard_plan (whole origins per rank when G >= ranks), [G,4] MIN allreduce (NCCL) per step."""
     import numpy as np
     import torch
 
     d = importlib.import_module("2048nn_b200.dist")
     eng = pkg.engine
-    gpath = os.path.join(ROOT, "tests", "golden", "c64b3_golden.npz")
     m = pkg.network.ConvNet(channels=64, blocks=3, precision="fp16")
     weights = "random-init (torch.manual_seed(0))"
-    if os.path.exists(gpath):
-        ng = np.load(gpath)
-        m.load_state_dict({k[len("sd_shipped/"):]: torch.from_numpy(np.array(ng[k])) for k in ng.files
-                           if k.startswith("sd_shipped/")})
+    sd = shipped_state_dict()
+    if sd is not None:
+        m.load_state_dict(sd)
         weights = "models/20200213 c64b3 checkpoint (fixture copy)"
     m.cuda().eval()
     blob = m.blob("fp16")
+    lc = pkg._lib.launch_count
     G, number = args.nn_origins * world, args.nn_lines
     origins = eng.init_boards(G, 4242, 0)  # synthetic fresh start boards, same on every rank
     for w in range(max(3, args.warmup)):
@@ -157,12 +309,14 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     moves = torch.zeros(1, dtype=torch.int64, device="cuda")
+    l0 = lc()
     e0.record()
     for k in range(args.steps):
         r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G)
-        moves += r["total_moves"]
+        moves += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
     e1.record()
     barrier()
+    launches = lc() - l0
     ms = e0.elapsed_time(e1)
     # end to end through the reference-facing call shape: host origins in, host [G,4] results out
     h_orig = origins.cpu().pin_memory()
@@ -181,10 +335,17 @@ def nn_policy_block(pkg, args, rank, world, barrier):
         _ = int(h_res[0, 0])  # host read of the step's result
     t1.record()
     barrier()
+    d.sum_over_ranks(moves)
+    d.sum_over_ranks(e2e_moves)
+    plan = d.shard_plan(G, number, rank, world)
+    how = ("replicated on every rank" if world > 1 and plan == (0, G, 0, number) else
+           "whole origins per rank (%d each)" % (plan[1] - plan[0]) if plan[2:] == (0, number) and world > 1 else
+           "lines of every root move split over the ranks" if world > 1 else "one GPU")
     # config 5: forward-only sweep point (1M boards per GPU from policy-game positions), device timed
     nb = 1 << 20
     fb = eng.init_boards(nb, 99, rank * nb)
-    m.forward_boards(fb, precision="fp16")
+    for _ in range(3):
+        m.forward_boards(fb, precision="fp16")
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -193,11 +354,16 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     f1.record()
     torch.cuda.synchronize()
     fwd_boards_per_s = 3 * nb / (f0.elapsed_time(f1) * 1e-3)
+    import copy
+    torch_base = torch_forward_baselines(pkg, copy.deepcopy(m), fb) if rank == 0 else None
+    # config 3 (one main game, mcts_nn number=50 per main move) and config 4 (256 main games in total, sharded)
+    game1 = main_games_block(pkg, blob, 1, number, args.game_steps, args.steps, args.warmup, 5000, 0, 1, barrier)
+    sp256 = main_games_block(pkg, blob, args.sp_games, number, args.sp_steps, args.steps, args.warmup, 7000, rank, world, barrier)
     return {"ms": ms, "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "e2e_moves": float(e2e_moves.item()),
-            "fwd_boards_per_s": fwd_boards_per_s,
-            "h2d": G * 8, "d2h": G * 4 * 8, "weights": weights,
-            "workload": f"mcts_nn: {G} origins (fresh boards) x 4 root moves x {number} c64b3 policy lines per step, "
-                        f"lines sharded over {world} GPU(s), [G,4] MIN allreduce per step"}
+            "fwd_boards_per_s": fwd_boards_per_s, "torch_base": torch_base, "launches": launches,
+            "h2d": G * 8, "d2h": G * 4 * 8, "weights": weights, "game1": game1, "sp256": sp256,
+            "workload": f"mcts_nn: {G} origins (fresh boards) x 4 root moves x {number} c64b3 policy lines per step over "
+                        f"{world} GPU(s): {how}, [G,4] MIN allreduce per step"}
 
 
 def train_step_block(pkg, args, rank, world, barrier):
@@ -248,6 +414,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nn-origins", type=int, default=256, help="mcts_nn origins per GPU per step (config 4: 256)")
     ap.add_argument("--nn-lines", type=int, default=50, help="policy lines per root move (config 3/4: 50)")
+    ap.add_argument("--game-steps", type=int, default=32, help="config 3: main moves of the single mcts_nn main game per step")
+    ap.add_argument("--sp-games", type=int, default=256, help="config 4: main games in TOTAL (sharded over the GPUs)")
+    ap.add_argument("--sp-steps", type=int, default=8, help="config 4: main moves per main game per step")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-policy block")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall target of the cpu_baseline sample")
@@ -306,11 +475,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     moves = torch.zeros((), dtype=torch.int64, device="cuda")
     barrier()
+    launches0 = pkg._lib.launch_count()
     e0.record()
     for k in range(args.steps):
         eng.playout_fixed(n, 2000 + k, gid_base, start=start, out=out)
     e1.record()
     barrier()
+    main_launches = pkg._lib.launch_count() - launches0  # kernels launched through the C ABI inside the timed region
     ms = e0.elapsed_time(e1)
     # move counts of the timed steps (recomputed outside the timed region from the last step,
     # plus an exact recount per seed would cost K more passes; moves/step is seed-stable to 1e-4)
@@ -341,9 +512,12 @@ def main():
     tr = train_step_block(pkg, args, rank, world, barrier) if not args.no_train else None
     clocks = sampler.stop() if rank == 0 else None
 
-    tmax = torch.tensor([ms, e2e_ms] + ([nn["ms"], nn["e2e_ms"]] if nn else [0.0, 0.0]) + ([tr["ms"], tr["ms_mixed"]] if tr else [0.0, 0.0]),
-                        dtype=torch.float64, device="cuda")
-    tot = torch.tensor([total_moves, float(e2e_moves)], dtype=torch.float64, device="cuda")
+    sp = nn["sp256"] if nn else None
+    tmax = torch.tensor([ms, e2e_ms] + ([nn["ms"], nn["e2e_ms"]] if nn else [0.0, 0.0]) + ([tr["ms"], tr["ms_mixed"]] if tr else [0.0, 0.0])
+                        + ([sp["ms"], sp["e2e_ms"]] if sp else [0.0, 0.0]), dtype=torch.float64, device="cuda")
+    tot = torch.tensor([total_moves, float(e2e_moves)] + ([sp["moves"], sp["mains"], sp["e2e_moves"], float(sp["launches"]),
+                                                           float(sp["h2d"]), float(sp["d2h"])] if sp else [0.0] * 6),
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -353,7 +527,10 @@ def main():
         nn["ms"], nn["e2e_ms"] = tl[2], tl[3]
     if tr:
         tr["ms"], tr["ms_mixed"] = tl[4], tl[5]
-    total_moves, e2e_moves = tot.tolist()
+    if sp:
+        sp["ms"], sp["e2e_ms"] = tl[6], tl[7]
+        sp["moves"], sp["mains"], sp["e2e_moves"], sp["launches"], sp["h2d"], sp["d2h"] = tot.tolist()[2:8]
+    total_moves, e2e_moves = tot.tolist()[:2]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -385,9 +562,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": args.steps,
+        "gpu_launches": main_launches,
         "roofline": {"bound": "sm_issue", "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
                      "frac": achieved / issue_peak, "traffic": traffic,
+                     "traffic_source": "committed ncu capture profiles/r01_k2_traffic_16m.json (same size), not measured in this run",
                      "note": "algorithmic 250 thread-instr/move x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); "
                              "the kernel is integer-issue bound, HBM sees only %.1f GB/s of %.0f"
                              % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
@@ -401,23 +579,60 @@ def main():
         npath = os.path.join(ROOT, "profiles", "r01_k4_traffic_nn_block.json")
         if os.path.exists(npath) and args.nn_origins == 256 and args.nn_lines == 50:
             nn_traffic = json.load(open(npath))["traffic_bytes_per_launch"]
+        fwd_tf = nn["fwd_boards_per_s"] * 5128704.0 / 1e12
+        forward_only = {"boards_per_s_per_gpu": nn["fwd_boards_per_s"], "boards": 1 << 20, "tflops_valid_taps": fwd_tf,
+                        "frac_of_sustained_peak": fwd_tf / peaks["bf16_tflops_sustained"]}
+        if nn["torch_base"]:
+            tb = nn["torch_base"]
+            best_torch = max(tb["eager_fp32"], tb["channels_last_bf16_autocast"])
+            forward_only["torch_baseline"] = {
+                "eager_fp32_boards_per_s": tb["eager_fp32"], "channels_last_bf16_autocast_boards_per_s": tb["channels_last_bf16_autocast"],
+                "speedup_vs_stronger_arm": nn["fwd_boards_per_s"] / best_torch, "note": tb["note"]}
         line["nn_policy"] = {
-            "metric": "playout moves/sec (c64b3 NN-policy, mcts_nn root evaluations)", "value": nn_value, "unit": UNIT,
+            "metric": NN_METRIC, "value": nn_value, "unit": UNIT,
             "ms_per_step": nn["ms"] / args.steps, "dtype": "fp16 operands / fp32 accumulate (tcgen05)",
             "config": {"workload": nn["workload"], "weights": nn["weights"], "scaling": "weak",
                        "l2": "compute-bound kernel: per-step inputs are 8 B per origin, the 0.5 MB weight image is L2-resident by design"},
             "e2e": {"value": nn["e2e_moves"] / (nn["e2e_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": nn["h2d"], "d2h_bytes_per_step": nn["d2h"]},
-            "gpu_launches": 2 * args.steps,
-            "forward_only": {"boards_per_s_per_gpu": nn["fwd_boards_per_s"], "boards": 1 << 20,
-                             "tflops_valid_taps": nn["fwd_boards_per_s"] * 5128704.0 / 1e12,
-                             "frac_of_sustained_peak": nn["fwd_boards_per_s"] * 5128704.0 / 1e12 / peaks["bf16_tflops_sustained"]},
+            "gpu_launches": nn["launches"],
+            "forward_only": forward_only,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": nn_traffic,
+                         "traffic_source": "committed ncu capture profiles/r01_k4_traffic_nn_block.json (default sizes), not measured in this run",
                          "note": "5,128,704 valid-tap FLOP per policy evaluation x evals/s on one GPU vs the %s "
-                                 "sustained dense bf16/fp16 GEMM peak; the kernel executes 1.2x that (y-padding rows)"
+                                 "sustained dense bf16/fp16 GEMM peak; the kernel executes 1.25x that (y-padding rows, K-doubled L0)"
                                  % peak_kind},
         }
+        g1, spb = nn["game1"], nn["sp256"]
+        line["mcts_nn_game"] = {
+            "metric": "BASELINE config 3: one main game driven by mcts_nn(number=%d), device-resident (b2048_selfplay_nn)" % args.nn_lines,
+            "ms_per_main_move": g1["ms"] / max(1.0, g1["mains"]), "value": g1["moves"] / (g1["ms"] * 1e-3), "unit": UNIT,
+            "main_moves_per_step": g1["mains"] / args.steps, "policy_moves_per_main_move": g1["moves"] / max(1.0, g1["mains"]),
+            "e2e": {"value": g1["e2e_moves"] / (g1["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": g1["h2d"],
+                    "d2h_bytes_per_step": g1["d2h"]},
+            "gpu_launches": g1["launches"],
+            "config": {"workload": "1 fresh main game x %d main moves per step, each main move = 4 root moves x %d policy lines "
+                                   "with the min-move early stop; %s" % (args.game_steps, args.nn_lines, nn["weights"]),
+                       "parallelism": "replicas only: 200 lines fit 7 of 148 SMs, the call is bound by the longest line (%d GPU(s) run "
+                                      "the same game)" % world}}
+        line["selfplay256"] = {
+            "metric": "BASELINE config 4: %d main games in TOTAL x mcts_nn(number=%d), device-resident, sharded by game" % (args.sp_games, args.nn_lines),
+            "value": spb["moves"] / (spb["ms"] * 1e-3), "unit": UNIT, "scaling": "strong",
+            "ms_per_step": spb["ms"] / args.steps, "main_moves_per_s": spb["mains"] / (spb["ms"] * 1e-3),
+            "e2e": {"value": spb["e2e_moves"] / (spb["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": spb["h2d"],
+                    "d2h_bytes_per_step": spb["d2h"]},
+            "gpu_launches": int(spb["launches"]),
+            "roofline": {"bound": "tensor", "achieved": spb["moves"] / (spb["ms"] * 1e-3) / world * 5128704.0 / 1e12, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": spb["moves"] / (spb["ms"] * 1e-3) / world * 5128704.0 / 1e12 / peak_tf, "traffic": None},
+            "config": {"workload": "%d main games (fresh boards) x %d main moves per step, %d policy lines per legal root move; main "
+                                   "games sharded over %d GPU(s) by game id, no collective on the data path (records gathered at the end)"
+                                   % (args.sp_games, args.sp_steps, args.nn_lines, world), "weights": nn["weights"]}}
+        if world == 1:
+            cores_nn = os.cpu_count() or 1
+            nv, ms_call, nsample = cpu_nn_rate(args.cpu_seconds, cores_nn)
+            line["nn_policy"]["cpu_baseline"] = {"value": nv, "unit": UNIT, "cores": cores_nn, "kind": "port",
+                                                 "ms_per_mcts_nn_call": ms_call, "sample": nsample}
     if tr:
         us = tr["ms"] * 1e3 / tr["steps"]
         flop = 2.0 * 7577600.0 * tr["batch"]  # in-bounds conv MACs of forward + data gradient + weight gradient per sample

@@ -35,6 +35,12 @@ def ng():
 
 
 @pytest.fixture(scope="session")
+def lg100k():
+    """>= 1e5 on-distribution boards with the unmodified reference network's log-probs (oracle/make_golden_logits.py)."""
+    return np.load(os.path.join(GOLDEN, "c64b3_logits_100k.npz"))
+
+
+@pytest.fixture(scope="session")
 def pkg():
     """The product package (directory name starts with a digit -> importlib)."""
     return importlib.import_module("2048nn_b200")

@@ -1,0 +1,128 @@
+"""GPU: re-entrancy of the C ABI -- concurrent launches from several host threads on several streams of one context
+give the serial results (atomic work-cursor pool, no shared scratch), and every call runs on its context's device
+without changing the caller's current device."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_dict_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def net(pkg, ng):
+    m = pkg.network.ConvNet(64, 3, precision="fp16")
+    m.load_state_dict(state_dict_from_golden(ng, "random"))
+    return m.cuda().eval()
+
+
+def _jobs(pkg, net, ng):
+    eng = pkg.engine
+    blob = net.blob("fp16")
+    origins = eng.init_boards(24, 5, 0)
+    boards = torch.from_numpy(ng["lg_boards"][:3000].view(np.int64).copy()).cuda()
+
+    def fixed(seed):
+        f, s, c = eng.playout_fixed(30000, seed, 0)
+        return torch.stack([f, s.to(torch.int64), c.to(torch.int64)])
+
+    def root_fixed(seed):
+        r = eng.mcts_fixed_lines(origins, 9, seed, 3, per_line=False, fused=True)
+        return torch.cat([r["logsum"].flatten(), r["count"].flatten().to(torch.int64), r["minmov"].flatten().to(torch.int64)])
+
+    def root_nn(seed):
+        r = eng.mcts_nn_lines(blob, "fp16", origins, 7, seed, 11)
+        return r["minmov"].flatten().to(torch.int64)
+
+    def games_nn(seed):
+        r = eng.playout_nn(blob, "fp16", 500, seed, 0)
+        return torch.stack([r["final"], r["score"].to(torch.int64), r["moves"].to(torch.int64)])
+
+    def forward(_seed):
+        return net.forward_boards(boards, precision="fp16")
+
+    def main_games(seed):
+        r = eng.selfplay_nn_games(blob, "fp16", 3, 4, seed, max_steps=6)
+        return torch.cat([r["final"], r["score"], r["steps"].to(torch.int64), r["boards"].flatten()])
+
+    return [fixed, root_fixed, root_nn, games_nn, forward, main_games]
+
+
+def test_concurrent_streams_and_threads_equal_serial(pkg, net, ng):
+    jobs = _jobs(pkg, net, ng)
+    plan = [(k % len(jobs), 100 + k) for k in range(36)]  # (job, seed)
+    serial = []
+    for j, seed in plan:
+        serial.append(jobs[j](seed).clone())
+    torch.cuda.synchronize()
+    assert pkg._lib.take_error_flag() == 0
+    results = [None] * len(plan)
+    errors = []
+
+    def worker(tid, nthreads):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for k in range(tid, len(plan), nthreads):
+                    j, seed = plan[k]
+                    results[k] = jobs[j](seed)
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t, 4)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for k, (a, b) in enumerate(zip(serial, results)):
+        assert torch.equal(a, b), ("launch %d (job %d) differs under concurrency" % (k, plan[k][0]))
+    assert pkg._lib.take_error_flag() == 0
+
+
+def test_launch_counter_counts_kernels(pkg):
+    n0 = pkg._lib.launch_count()
+    pkg.engine.playout_fixed(1000, 1, 0)
+    assert pkg._lib.launch_count() - n0 == 1
+    o = pkg.engine.init_boards(4, 1, 0)
+    n1 = pkg._lib.launch_count()
+    pkg.engine.mcts_fixed_lines(o, 5, 1, 0)
+    assert pkg._lib.launch_count() - n1 == 2  # root moves + the playout kernel
+
+
+def test_calls_keep_the_callers_current_device(pkg):
+    import ctypes as C
+
+    L = pkg._lib
+    lib = L.load_library()
+    cur = torch.cuda.current_device()
+    h = C.c_void_p()
+    L.check(lib.b2048_create(cur, C.byref(h)))
+    assert torch.cuda.current_device() == cur
+    L.check(lib.b2048_destroy(h))
+    bad = C.c_void_p()
+    assert lib.b2048_create(torch.cuda.device_count() + 3, C.byref(bad)) != 0
+    assert b"no such CUDA device" in lib.b2048_last_error()
+    assert torch.cuda.current_device() == cur
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_context_of_another_gpu_from_one_process(pkg):
+    # a context of GPU 1 driven from a thread whose current device is GPU 0: same games, current device untouched
+    assert torch.cuda.current_device() == 0
+    a = pkg.engine.playout_fixed(5000, 77, 0, device="cuda:0")
+    b = pkg.engine.playout_fixed(5000, 77, 0, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    for x, y in zip(a, b):
+        assert x.device.index == 0 and y.device.index == 1 and torch.equal(x.cpu(), y.cpu())
+    o1 = pkg.engine.init_boards(6, 3, 0, device="cuda:1")
+    r1 = pkg.engine.mcts_fixed_lines(o1, 5, 3, 0)
+    r0 = pkg.engine.mcts_fixed_lines(o1.to("cuda:0"), 5, 3, 0)
+    assert torch.equal(r1["lmoves"].cpu(), r0["lmoves"].cpu()) and torch.cuda.current_device() == 0
