@@ -31,6 +31,7 @@ _SIGS = {
     "b2048_num_sms": (C.c_int, [P]),
     "b2048_launch_count": (i64, [P]),
     "b2048_set_playout_variant": (C.c_int, [P, C.c_int]),
+    "b2048_set_latency_mode": (C.c_int, [P, C.c_int]),
     "b2048_take_error_flag": (C.c_int, [P, P, C.POINTER(C.c_int)]),
     "b2048_tables": (C.c_int, [P, P, P, P, P, P, P]),
     "b2048_move_batch": (C.c_int, [P, P, P, C.c_int, P, P, P, i64, P]),

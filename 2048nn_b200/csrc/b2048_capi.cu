@@ -61,6 +61,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->legal, 65536));
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
     c->k2_variant = 1;
+    c->tc_wide = 1;
     CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMemset(c->counters, 0, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
@@ -84,6 +85,12 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
@@ -112,6 +119,11 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
 
 extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
 extern "C" int64_t b2048_launch_count(const b2048_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
+
+extern "C" int b2048_set_latency_mode(b2048_ctx *c, int on) {
+    c->tc_wide.store(on ? 1 : 0);
+    return 0;
+}
 
 extern "C" int b2048_set_playout_variant(b2048_ctx *c, int variant) {
     if (variant != 0 && variant != 1) return fail_msg("b2048_set_playout_variant: variant must be 0 or 1");
@@ -390,6 +402,14 @@ static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boa
     p.counter = take_counters(c, 1);
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
     int grid = grid_for(n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+    if (!dbg && !bf16 && c->tc_wide.load() && n <= (int64_t)c->num_sms * tc::TILE_BOARDS) {
+        // latency mode: at most one 32-board tile per SM -> one tile-set per CTA, all 16 worker warps on its epilogue
+        grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
+        tc::tc_persistent_kernel<tc::FwdWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            p, (const uint8_t *)blob, nullptr, -1, (long)n);
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (dbg)
         tc::tc_persistent_kernel<tc::FwdWork, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
             p, (const uint8_t *)blob, dbg, dbg_layer, (long)n);
@@ -457,9 +477,17 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
             grid = p.single_set ? grid_for(total, tc::TILE_BOARDS, c->num_sms)
                                 : grid_for(total, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
         }
+        const bool wide = p.single_set && models == 1 && precision == B2048_PREC_FP16_TC && c->tc_wide.load();
         if (p.main_mode) {
             if (precision != B2048_PREC_FP16_TC) return fail_msg("b2048_selfplay_nn: precision must be FP32 or FP16_TC");
-            tc::tc_persistent_kernel<MainWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            if (wide)
+                tc::tc_persistent_kernel<MainWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<MainWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        } else if (wide) {
+            tc::tc_persistent_kernel<PlayWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
         } else if (precision == B2048_PREC_BF16_TC)
             tc::tc_persistent_kernel<PlayWork, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(

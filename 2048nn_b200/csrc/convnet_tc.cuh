@@ -73,8 +73,8 @@ constexpr int SM_TAIL = SM_RING + RING * CHUNK_BYTES;      // fp32 tail copy
 constexpr int SM_BOARDS = SM_TAIL + TAIL_FLOATS * 4;       // NSETS x 32 x u64
 constexpr int SM_LOGITS = SM_BOARDS + NSETS * 32 * 8;      // NSETS x 32 x 4 f32
 constexpr int SM_RUN = SM_LOGITS + NSETS * 32 * 16;        // NSETS x {run flag, debug base}
-constexpr int SM_BARS = SM_RUN + 32 * NSETS;                      // mbarriers: full[RING] empty[RING] acc[NSETS] act[NSETS]
-constexpr int SM_TMEMPTR = SM_BARS + 8 * (2 * RING + 2 * NSETS);
+constexpr int SM_BARS = SM_RUN + 32 * NSETS;                      // mbarriers: full[RING] empty[RING] acc[NSETS] act[NSETS] idle[NSETS]
+constexpr int SM_TMEMPTR = SM_BARS + 8 * (2 * RING + 3 * NSETS);
 constexpr int SM_CAND = SM_TMEMPTR + 16;                   // NSETS x 32 slots x 64 B: work-policy scratch (candidate moves)
 constexpr int SM_TOTAL = SM_CAND + NSETS * 32 * 64;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
@@ -215,17 +215,28 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 }
 
 struct Bars {
-    uint32_t full0, empty0, acc0, act0;
+    uint32_t full0, empty0, acc0, act0, idle0;
     __device__ __forceinline__ explicit Bars(uint32_t sm_base) {
         full0 = sm_base + SM_BARS;
         empty0 = full0 + 8 * RING;
         acc0 = empty0 + 8 * RING;
         act0 = acc0 + 8 * NSETS;
+        idle0 = act0 + 8 * NSETS;
     }
 };
 
+// What a tile-set does in one iteration (Work::step's result, published in s_run before the set's first act arrival):
+//   RUN_STOP  the set is finished for good
+//   RUN_FWD   one forward of its 32 boards
+//   RUN_IDLE  nothing to evaluate right now, but work may still arrive (device-resident main games: the line queue is
+//             momentarily empty).  The set skips the forward; the three control warps (producer, two MMA issuers) each
+//             acknowledge on idle[set], so the set cannot publish its next decision before all of them have read this
+//             one -- and the MMA warps, which serve both sets, are never held up by a set that is waiting for work.
+constexpr int RUN_STOP = 0, RUN_FWD = 1, RUN_IDLE = 2;
+constexpr int N_CONTROL_WARPS = 3;
+
 // ---- CTA setup / teardown ----------------------------------------------------------------------
-__device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *blob, uint32_t &tmem_base) {
+__device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *blob, uint32_t &tmem_base, int group_warps) {
     uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sm_base = smem_u32(sm);
     const int tid = threadIdx.x;
@@ -241,7 +252,8 @@ __device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *b
         }
         for (int i = 0; i < NSETS; i++) {
             mbar_init(b.acc0 + 8 * i, 2);            // tcgen05.commit of the two MMA-issuing warps
-            mbar_init(b.act0 + 8 * i, GROUP_WARPS);  // one arrival per worker warp of the set
+            mbar_init(b.act0 + 8 * i, group_warps);  // one arrival per worker warp of the set
+            mbar_init(b.idle0 + 8 * i, N_CONTROL_WARPS);
         }
         fence_mbar_init();
     }
@@ -264,25 +276,34 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
 // One "iteration" = one forward of every active set.  Each 24 KB chunk (layer, dy) is loaded ONCE per
 // iteration and consumed by both sets back to back, so the ring's two slots cover twice the MMA time.
 // Mirrors the MMA warp's control flow (same run flags, same chunk order).
-__device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob) {
+__device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob, int nsets) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
     const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
     const int lane = threadIdx.x & 31;
     bool active[NSETS];
-    uint32_t iter[NSETS];
-    for (int i = 0; i < NSETS; i++) active[i] = true, iter[i] = 0;
+    uint32_t ph[NSETS];  // act phases of the set consumed so far: 7 per forward, 1 per idle iteration
+    for (int i = 0; i < NSETS; i++) active[i] = i < nsets, ph[i] = 0;
     uint32_t prod = 0;
     for (;;) {
-        bool any = false;
+        bool any = false, load = false;
         for (int set = 0; set < NSETS; set++) {
             if (!active[set]) continue;
-            // the set's workers publish "run" before their first act_ready arrival of the iteration
-            mbar_wait(bars.act0 + 8 * set, (iter[set] * N_LAYERS) & 1);
-            if (!s_run[8 * set]) active[set] = false;
-            else any = true, iter[set]++;
+            // the set's workers publish their decision before their first act arrival of the iteration
+            mbar_wait(bars.act0 + 8 * set, ph[set] & 1);
+            const int r = s_run[8 * set];
+            if (r == RUN_STOP) {
+                active[set] = false;
+            } else if (r == RUN_IDLE) {
+                any = true, ph[set] += 1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars.idle0 + 8 * set);
+            } else {
+                any = true, load = true, ph[set] += N_LAYERS;
+            }
         }
         if (!any) break;
+        if (!load) continue;  // every running set idles: the MMA warps consume no chunk in this iteration either
         if (lane == 0) {
             for (int c = 0; c < N_CHUNKS; c++) {
                 const uint32_t slot = prod % RING, use = prod / RING;
@@ -337,13 +358,13 @@ __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32
     }
 }
 
-__device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16) {
+__device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int nsets) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
     const volatile int *s_run = reinterpret_cast<const volatile int *>(sm + SM_RUN);
-    bool active[NSETS];
+    bool active[NSETS], skip[NSETS];
     uint32_t phase[NSETS];
-    for (int i = 0; i < NSETS; i++) active[i] = true, phase[i] = 0;
+    for (int i = 0; i < NSETS; i++) active[i] = i < nsets, skip[i] = false, phase[i] = 0;
     uint32_t cons = 0;
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
     int trace_iter = -1;
@@ -357,15 +378,25 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16) {
                 bool have_chunk = false;
                 for (int set = 0; set < NSETS; set++) {
                     if (!active[set]) continue;
+                    if (l == 0 && dyi == 0) skip[set] = false;
+                    if (skip[set]) continue;  // the set idles in this iteration
                     if (dyi == 0) {
                         mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
                         if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
                         if (l == 0) {
-                            if (!s_run[8 * set]) {
+                            const int r = s_run[8 * set];
+                            if (r == RUN_STOP) {
                                 active[set] = false;
                                 continue;
                             }
                             any = true;
+                            if (r == RUN_IDLE) {
+                                skip[set] = true;
+                                phase[set]++;  // an idle iteration has this one act phase
+                                __syncwarp();
+                                if ((threadIdx.x & 31) == 0) mbar_arrive(bars.idle0 + 8 * set);
+                                continue;
+                            }
                         }
                     }
                     if (!have_chunk) {
@@ -398,22 +429,22 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16) {
 //   KEEP_RES this output is a block input: remember it (packed fp16) in `res`
 //   LAST     last conv: do not write back; accumulate the 1x1 head conv on the fp32 values instead
 // row0/row1, bias, tail are 32-bit shared-space addresses.
-template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG, bool BF16>
+template <bool ADD_RES, bool KEEP_RES, bool LAST, bool DBG, bool BF16, int NX>
 __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uint32_t sw16, uint32_t bias, uint32_t tail,
-                                               uint32_t acc0, uint32_t (&res)[2][32], float (&head_acc)[2][4],
+                                               uint32_t acc0, uint32_t (&res)[NX][32], float (&head_acc)[NX][4],
                                                float *dbg0) {
     // Both rows drained 8 columns at a time with one tcgen05.wait::ld per step.  Register budget: res (64)
     // dominates.  Measured on B200: 16-column steps and per-row / double-buffered pipelining were not faster.
 #pragma unroll
     for (int c = 0; c < 8; c++) {  // 16-byte chunk = 8 channels
-        float v[2][8];
+        float v[NX][8];
         tmem_ld8(acc0 + (uint32_t)(c * 8), reinterpret_cast<uint32_t *>(v[0]));
-        tmem_ld8(acc0 + (uint32_t)(64 + c * 8), reinterpret_cast<uint32_t *>(v[1]));
+        if (NX == 2) tmem_ld8(acc0 + (uint32_t)(64 + c * 8), reinterpret_cast<uint32_t *>(v[NX - 1]));
         const float4 b0 = lds_f4(bias + c * 32), b1 = lds_f4(bias + c * 32 + 16);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         tmem_ld_wait();
 #pragma unroll
-        for (int xi = 0; xi < 2; xi++) {
+        for (int xi = 0; xi < NX; xi++) {
             uint32_t pw[4];
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
@@ -457,20 +488,26 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
 //     static size_t blob_offset(const Params&);   // byte offset of this CTA's weight image (multi-model launches)
 //     static void init(State&, const Params&, int set);
 //     // consume the previous forward's outputs (unless first), then provide the next 32 boards.
-//     // returns false when the set is finished.
-//     static bool step(const Params&, State&, bool first, const float *logits, unsigned long long *boards,
+//     // returns RUN_FWD (forward them), RUN_STOP (the set is finished) or RUN_IDLE (nothing now, ask again); bool works
+//     // for policies that never idle (true = RUN_FWD, false = RUN_STOP).
+//     static int step(const Params&, State&, bool first, const float *logits, unsigned long long *boards,
 //                      int lane, long &dbg_base, uint8_t *scratch);
 //     // called right after the boards are published: start long-latency work for the NEXT step() so that it
 //     // overlaps the forward (scratch = 64 B of shared memory per slot)
 //     static void prefetch(const Params&, State&, uint8_t *scratch, int lane); };
-template <class Work, bool DBG, bool BF16>
+// WIDE = latency mode (one tile-set per CTA): all 16 worker warps serve set 0, one (x, y, board) row per thread instead
+// of two, which halves the epilogue -- the part of a 32-board forward that the tensor pipe has to wait for.
+template <class Work, bool DBG, bool BF16, bool WIDE>
 __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, const typename Work::Params &wp, int set,
                                             int j, float *dbg, int dbg_layer, long dbg_n) {
+    constexpr int NX = WIDE ? 1 : 2;                          // rows (board columns x) per thread
+    constexpr int GW = WIDE ? WORKER_WARPS : GROUP_WARPS;     // worker warps of this group
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;   // TMEM lane quarter this warp may read == board row y
-    const int xg = j >> 2;    // rows handled: x in {2*xg, 2*xg+1}
+    const int xg = j >> 2;    // rows handled: x in {2*xg, 2*xg+1} (WIDE: x = xg)
+    const int x0 = WIDE ? xg : 2 * xg;
     uint8_t *act = sm + SM_ACT + set * ACT_BYTES;
     const float *tail = reinterpret_cast<const float *>(sm + SM_TAIL);
     unsigned long long *s_boards = reinterpret_cast<unsigned long long *>(sm + SM_BOARDS) + set * 32;
@@ -479,40 +516,49 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
     volatile long *s_dbgbase = reinterpret_cast<volatile long *>(sm + SM_RUN + 32 * set + 8);
     const uint32_t bar_acc = bars.acc0 + 8 * set, bar_act = bars.act0 + 8 * set;
     // accumulators of this thread's two rows: lane quarter q, column blocks x0 and x0+1 of the set
-    const uint32_t acc0 = tmem_base + (uint32_t)(set * 256 + xg * 128) + ((uint32_t)(q * 32) << 16);
-    uint8_t *row0 = act + (size_t)act_row(2 * xg, q, lane) * ROW_BYTES;
-    uint8_t *row1 = act + (size_t)act_row(2 * xg + 1, q, lane) * ROW_BYTES;
+    const uint32_t acc0 = tmem_base + (uint32_t)(set * 256 + x0 * 64) + ((uint32_t)(q * 32) << 16);
+    uint8_t *row0 = act + (size_t)act_row(x0, q, lane) * ROW_BYTES;
+    uint8_t *row1 = act + (size_t)act_row(WIDE ? x0 : x0 + 1, q, lane) * ROW_BYTES;
     const int sw = lane & 7;  // SWIZZLE_128B phase of both rows (row index % 8 == lane % 8)
     const int bar_id = 1 + set;
     typename Work::State ws;
     if (j == 0) Work::init(ws, wp, set);
-    uint32_t phase = 0;
+    uint32_t phase = 0, idle_phase = 0;
     bool first = true;
-    uint32_t res[2][32];  // residual input of the current block, packed fp16
+    uint32_t res[NX][32];  // residual input of the current block, packed fp16
     int trace_iter = -1;
     for (;;) {
         trace_iter++;
         if (j == 0) {
             long db = 0;
-            bool run = Work::step(wp, ws, first, s_logits, s_boards, lane, db, sm + SM_CAND + set * 2048);
+            const int run = (int)Work::step(wp, ws, first, s_logits, s_boards, lane, db, sm + SM_CAND + set * 2048);
             if (lane == 0) {
-                *s_run = run ? 1 : 0;
+                *s_run = run;
                 *s_dbgbase = db;
             }
         }
         first = false;
-        named_bar(bar_id, GROUP_WARPS * 32);
-        const bool run = *s_run != 0;
-        if (!run) {
+        named_bar(bar_id, GW * 32);
+        const int run = *s_run;
+        if (run == RUN_STOP) {
             if (lane == 0) mbar_arrive(bar_act);  // tells the MMA / producer warps that this set is done
             break;
+        }
+        if (run == RUN_IDLE) {
+            // no board to evaluate now: publish the decision (act), wait until the producer and both MMA warps have
+            // read it (idle), then ask the work policy again
+            if (lane == 0) mbar_arrive(bar_act);
+            mbar_wait(bars.idle0 + 8 * set, idle_phase & 1);
+            idle_phase++;
+            if (j == 0) __nanosleep(1000);  // poll interval of a set that waits for work
+            continue;
         }
         // ---- encode: one-hot rows (channels [0,16) and again [16,32) for the hi/lo weight split) --------
         {
             const unsigned long long brd = s_boards[lane];
 #pragma unroll
-            for (int xi = 0; xi < 2; xi++) {
-                const int t = (int)((brd >> (4 * (q * 4 + 2 * xg + xi))) & 0xF);
+            for (int xi = 0; xi < NX; xi++) {
+                const int t = (int)((brd >> (4 * (q * 4 + x0 + xi))) & 0xF);
                 uint8_t *row = xi ? row1 : row0;
                 const uint32_t one = (BF16 ? 0x3F80u : 0x3C00u) << ((t & 1) * 16);  // 1.0 in the right half-word
                 const int wsel = (t & 7) >> 1;
@@ -532,9 +578,9 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
         // long-latency preparation of the NEXT step (candidate moves) overlaps the first layer's MMAs
         if (j == 0) Work::prefetch(wp, ws, sm + SM_CAND + set * 2048, lane);
 
-        float head_acc[2][4];
+        float head_acc[NX][4];
 #pragma unroll
-        for (int xi = 0; xi < 2; xi++)
+        for (int xi = 0; xi < NX; xi++)
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++) head_acc[xi][c4] = tail[TAIL_B7 + c4];
         float *dbg0 = nullptr;
@@ -546,19 +592,19 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             tc_fence_after();
             if (DBG) {
                 const long gb = *s_dbgbase + lane;
-                dbg0 = (dbg && dbg_layer == l && gb < dbg_n) ? dbg + gb * 1024 + (q * 4 + 2 * xg) : nullptr;
+                dbg0 = (dbg && dbg_layer == l && gb < dbg_n) ? dbg + gb * 1024 + (q * 4 + x0) : nullptr;
             }
             {
                 const uint32_t r0a = smem_u32(row0), r1a = smem_u32(row1), sw16 = (uint32_t)sw << 4;
                 const uint32_t ba = smem_u32(bias), ta = smem_u32(tail);
                 if (l == 0)
-                    epilogue_layer<false, true, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<false, true, false, DBG, BF16, NX>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (l & 1)
-                    epilogue_layer<false, false, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<false, false, false, DBG, BF16, NX>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (l < N_LAYERS - 1)
-                    epilogue_layer<true, true, false, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<true, true, false, DBG, BF16, NX>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else
-                    epilogue_layer<true, false, true, DBG, BF16>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
+                    epilogue_layer<true, false, true, DBG, BF16, NX>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
             }
             tc_fence_before();
             if (l < N_LAYERS - 1) {
@@ -574,39 +620,39 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
         {
             const uint32_t hb = smem_u32(act + SLAB_ROWS * ROW_BYTES);
 #pragma unroll
-            for (int xi = 0; xi < 2; xi++) {
-                const int pos = q * 4 + xg * 2 + xi;
+            for (int xi = 0; xi < NX; xi++) {
+                const int pos = q * 4 + x0 + xi;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++)
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(hb + (uint32_t)(lane * HEAD_STRIDE + c4 * 16 + pos) * 4),
                                  "f"(fmaxf(head_acc[xi][c4], 0.f))
                                  : "memory");
             }
-            named_bar(bar_id, GROUP_WARPS * 32);
-            const int t = j * 32 + lane, b = t >> 3, part = t & 7;
+            named_bar(bar_id, GW * 32);
+            constexpr int PARTS = GW, PER = 64 / PARTS;  // threads per board, inputs per thread
+            const int t = j * 32 + lane, b = t / PARTS, part = t % PARTS;
             const uint32_t ta = smem_u32(tail);
             float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < PER; i++) {
                 float x;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(hb + (uint32_t)(b * HEAD_STRIDE + part * 8 + i) * 4));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(hb + (uint32_t)(b * HEAD_STRIDE + part * PER + i) * 4));
 #pragma unroll
                 for (int o = 0; o < 4; o++) {
                     float w;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(ta + (uint32_t)(TAIL_FCW + o * 64 + part * 8 + i) * 4));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(ta + (uint32_t)(TAIL_FCW + o * 64 + part * PER + i) * 4));
                     z[o] = fmaf(x, w, z[o]);
                 }
             }
 #pragma unroll
             for (int o = 0; o < 4; o++) {
-                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 1);
-                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 2);
-                z[o] += __shfl_xor_sync(0xffffffffu, z[o], 4);
+#pragma unroll
+                for (int sh = 1; sh < PARTS; sh <<= 1) z[o] += __shfl_xor_sync(0xffffffffu, z[o], sh);
             }
             if (part == 0)
                 *reinterpret_cast<float4 *>(s_logits + b * 4) =
                     make_float4(z[0] + tail[TAIL_FCB + 0], z[1] + tail[TAIL_FCB + 1], z[2] + tail[TAIL_FCB + 2], z[3] + tail[TAIL_FCB + 3]);
-            named_bar(bar_id, GROUP_WARPS * 32);
+            named_bar(bar_id, GW * 32);
         }
         // the owner warp consumes s_logits in Work::step at the top of the loop; the other warps wait for
         // it at the group barrier there, so the image is not re-encoded before the head has been read.
@@ -614,21 +660,23 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
 }
 
 // Generic persistent kernel: producer + MMA issuer + NSETS worker groups.
-template <class Work, bool DBG, bool BF16 = false>
+template <class Work, bool DBG, bool BF16 = false, bool WIDE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float *dbg, int dbg_layer, long dbg_n) {
     extern __shared__ uint8_t smem_raw[];
     blob += Work::blob_offset(wp);
     uint32_t tmem_base;
-    uint8_t *sm = tc_setup(smem_raw, blob, tmem_base);
+    uint8_t *sm = tc_setup(smem_raw, blob, tmem_base, WIDE ? WORKER_WARPS : GROUP_WARPS);
     const int warp = threadIdx.x >> 5;
+    constexpr int nsets = WIDE ? 1 : NSETS;
     if (warp < WORKER_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WORKER_REGS));
-        worker_loop<Work, DBG, BF16>(sm, tmem_base, wp, warp / GROUP_WARPS, warp % GROUP_WARPS, dbg, dbg_layer, dbg_n);
+        if (WIDE) worker_loop<Work, DBG, BF16, true>(sm, tmem_base, wp, 0, warp, dbg, dbg_layer, dbg_n);
+        else worker_loop<Work, DBG, BF16, false>(sm, tmem_base, wp, warp / GROUP_WARPS, warp % GROUP_WARPS, dbg, dbg_layer, dbg_n);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
-        if (warp == PRODUCER_WARP) producer_loop(sm, blob);
-        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop(sm, warp - MMA_WARP, BF16);
+        if (warp == PRODUCER_WARP) producer_loop(sm, blob, nsets);
+        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop(sm, warp - MMA_WARP, BF16, nsets);
     }
     tc_teardown(tmem_base);
 }

@@ -367,8 +367,9 @@ __device__ __forceinline__ void mg_start_line(const NNPlayParams &p, GameSlot &g
 // Warp-level service routine of the main-game mode, called by all 32 lanes of a slot-owning warp after the move
 // phase: (1) lanes whose line closed a main step advance that game and queue its next lines (one closer at a time,
 // the warp writes the items together), (2) free slots claim queued lines (one CAS per warp), (3) a warp with nothing
-// live waits while main games are still running elsewhere.  `has_slot`: this lane owns a game slot.
-__device__ __noinline__ void mg_service(const NNPlayParams &p, GameSlot &g, bool has_slot, bool &queue_empty, int lane) {
+// live waits while main games are still running elsewhere (`spin`; the tensor-core kernel passes false and idles the
+// tile-set through its RUN_IDLE protocol instead, because its MMA warps serve two sets).  `has_slot`: this lane owns a slot.
+__device__ __noinline__ void mg_service(const NNPlayParams &p, GameSlot &g, bool has_slot, bool &queue_empty, int lane, bool spin) {
     MainQueue *q = p.mgq;
     for (;;) {
         unsigned cm = __ballot_sync(0xffffffffu, has_slot && g.closing);
@@ -426,7 +427,7 @@ __device__ __noinline__ void mg_service(const NNPlayParams &p, GameSlot &g, bool
         }
         const unsigned live = __ballot_sync(0xffffffffu, has_slot && g.live);
         const unsigned open = __ballot_sync(0xffffffffu, has_slot && !queue_empty);
-        if (live || !open) return;
+        if (live || !open || !spin) return;
         __nanosleep(512);  // all slots free, main games still running on other SMs: poll the queue
     }
 }
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
         if (t == 0) s_live = 0;
         __syncthreads();
         if (p.main_mode) {
-            if (t < 32) mg_service(p, g, t < CN_BOARDS_PER_CTA, queue_empty, t);
+            if (t < 32) mg_service(p, g, t < CN_BOARDS_PER_CTA, queue_empty, t, true);
         } else if (t < CN_BOARDS_PER_CTA) {
             if (!g.live && !queue_empty) queue_empty = !nn_fetch(p, g);
         }
@@ -540,21 +541,23 @@ struct PlayWorkT {
         c->legal = legal;
         c->gmin = (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff;
     }
-    __device__ static bool step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
-                                int lane, long &dbg_base, uint8_t *scratch) {
+    __device__ static int step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
+                               int lane, long &dbg_base, uint8_t *scratch) {
         dbg_base = 0;
         if (!first && st.g.live)
             nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
-        if (MAIN) mg_service(p, st.g, true, st.queue_empty, lane);
+        if (MAIN) mg_service(p, st.g, true, st.queue_empty, lane, false);
         else if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
         s_boards[lane] = st.g.live ? st.g.board : 0ULL;
         const unsigned any = __ballot_sync(0xffffffffu, st.g.live);
+        if (MAIN && !any && __ballot_sync(0xffffffffu, !st.queue_empty))
+            return tc::RUN_IDLE;  // no line here now, main games still running: lines may be queued any moment
         if (!any && p.move_counter) {
             u32 m = st.moves_done;
             for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
             if (lane == 0 && m) atomicAdd(p.move_counter, (unsigned long long)m);
         }
-        return any != 0;
+        return any ? tc::RUN_FWD : tc::RUN_STOP;
     }
 };
 typedef PlayWorkT<false> PlayWork;

@@ -282,6 +282,11 @@ def set_playout_variant(variant, device=None):
     L.check(L.load_library().b2048_set_playout_variant(L.ctx(device), int(variant)))
 
 
+def set_latency_mode(on, device=None):
+    """Small tensor-core launches: 16-warp one-set kernel variant on (default) / off (b2048_set_latency_mode)."""
+    L.check(L.load_library().b2048_set_latency_mode(L.ctx(device), int(bool(on))))
+
+
 def num_sms(device=None):
     """SM count of the context's device (persistent kernels launch one CTA per SM)."""
     return int(L.load_library().b2048_num_sms(L.ctx(device)))

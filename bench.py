@@ -31,6 +31,16 @@ UNIT = "moves/s"
 INSTR_PER_MOVE = 250.0  # algorithmic thread-instructions per accepted move
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """progress on stderr (stdout carries exactly the one JSON line)"""
+    if os.environ.get("RANK", "0") == "0":
+        sys.stderr.write("[bench %7.2fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -238,9 +248,11 @@ def main_games_block(pkg, blob, G_total, number, main_steps, steps, warmup, seed
         return eng.selfplay_nn_games(blob, "fp16", n_local, number, seed, starts=starts, game_id_base=g0, games_total=G_total,
                                      max_steps=main_steps)
 
+    log("main games: %d total, %d here, %d main moves per step: warm-up" % (G_total, n_local, main_steps))
     for w in range(max(3, warmup)):
         play(seed0 + w)
     barrier()
+    log("main games: timed region")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     moves = torch.zeros(1, dtype=torch.int64, device="cuda")
     mains = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -268,6 +280,7 @@ def main_games_block(pkg, blob, G_total, number, main_steps, steps, warmup, seed
         h2d = n_local * 8
         d2h = hb.numel() * 8 + hr.numel() * 4 + hs.numel() * 8 + 8
     barrier()
+    log("main games: end-to-end region")
     t0.record()
     for k in range(steps):
         if n_local:
@@ -304,6 +317,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     lc = pkg._lib.launch_count
     G, number = args.nn_origins * world, args.nn_lines
     origins = eng.init_boards(G, 4242, 0)  # synthetic fresh start boards, same on every rank
+    log("nn_policy: root evaluations")
     for w in range(max(3, args.warmup)):
         d.mcts_nn_sharded(blob, "fp16", origins, number, 100 + w, 0)
     barrier()
@@ -342,6 +356,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
            "whole origins per rank (%d each)" % (plan[1] - plan[0]) if plan[2:] == (0, number) and world > 1 else
            "lines of every root move split over the ranks" if world > 1 else "one GPU")
     # config 5: forward-only sweep point (1M boards per GPU from policy-game positions), device timed
+    log("nn_policy: forward only + torch baselines")
     nb = 1 << 20
     fb = eng.init_boards(nb, 99, rank * nb)
     for _ in range(3):
@@ -357,6 +372,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     import copy
     torch_base = torch_forward_baselines(pkg, copy.deepcopy(m), fb) if rank == 0 else None
     # config 3 (one main game, mcts_nn number=50 per main move) and config 4 (256 main games in total, sharded)
+    log("nn_policy: config 3 / config 4 main games")
     game1 = main_games_block(pkg, blob, 1, number, args.game_steps, args.steps, args.warmup, 5000, 0, 1, barrier)
     sp256 = main_games_block(pkg, blob, args.sp_games, number, args.sp_steps, args.steps, args.warmup, 7000, rank, world, barrier)
     return {"ms": ms, "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "e2e_moves": float(e2e_moves.item()),
@@ -508,8 +524,11 @@ def main():
     e2e_ms = t0.elapsed_time(t1)
 
     # ---- second headline: c64b3 NN-policy playouts (mcts_nn root evaluations, config 3/4 shape) ----
+    log("fixed-order block done")
     nn = nn_policy_block(pkg, args, rank, world, barrier) if not args.no_nn else None
+    log("training block")
     tr = train_step_block(pkg, args, rank, world, barrier) if not args.no_train else None
+    log("blocks done")
     clocks = sampler.stop() if rank == 0 else None
 
     sp = nn["sp256"] if nn else None
@@ -630,6 +649,7 @@ def main():
                                    % (args.sp_games, args.sp_steps, args.nn_lines, world), "weights": nn["weights"]}}
         if world == 1:
             cores_nn = os.cpu_count() or 1
+            log("cpu baseline of the NN path (%d threads)" % cores_nn)
             nv, ms_call, nsample = cpu_nn_rate(args.cpu_seconds, cores_nn)
             line["nn_policy"]["cpu_baseline"] = {"value": nv, "unit": UNIT, "cores": cores_nn, "kind": "port",
                                                  "ms_per_mcts_nn_call": ms_call, "sample": nsample}

@@ -69,6 +69,11 @@ int64_t b2048_launch_count(const b2048_ctx *ctx);
  * move; 0 = the L,U,D,R attempt cascade.  Both are bit-exact; the switch exists for A/B measurements. */
 int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
 
+/* Tensor-core launches small enough for one 32-board tile per SM (forward of <= 32 x #SMs boards, root evaluations /
+ * main games with <= 32 x #SMs lines) run a latency variant of the kernel: one tile-set per CTA with all 16 worker warps
+ * on its epilogue.  on = 0 switches it off (A/B measurements; results are identical either way).  Default: on. */
+int b2048_set_latency_mode(b2048_ctx *ctx, int on);
+
 /* Device error flag: set when a spawn met countzero == 0 (the reference raises ValueError from
  * randrange(0), board.py:87).  Reads and clears it into *out_host; synchronises `stream`. */
 int b2048_take_error_flag(b2048_ctx *ctx, void *stream, int *out_host);

@@ -33,6 +33,22 @@ same_sp = all(np.array_equal(recs[g]["boards"], hb[g, :steps[g]]) for g in range
 ok &= same_sp
 if rank == 0:
     print(f"selfplay_batch sharded over {world} ranks {'ok' if same_sp else 'MISMATCH'} ({mv} playout moves)", flush=True)
+# NN-policy main games (config 4 shape): device-resident, sharded by game over the ranks == one GPU playing them all
+mr = pkg.network.ConvNet(64, 3, precision="fp16")
+mr.load_state_dict({k[len("sd_random/"):]: torch.from_numpy(np.array(ng[k])) for k in ng.files if k.startswith("sd_random/")})
+mr.cuda().eval()
+Gn = 2 * world + 1
+recs_nn, mv_nn = pkg.selfplay.selfplay_batch(Gn, 5, mr, seed=21, precision="fp16")
+one_nn = eng.selfplay_nn_games(mr.blob("fp16"), "fp16", Gn, 5, 21, max_steps=16384)
+st_nn = one_nn["steps"].cpu().numpy()
+hb_nn = one_nn["boards"].cpu().numpy().view(np.uint64)
+hr_nn = one_nn["results"].cpu().numpy()
+same_nn = all(np.array_equal(recs_nn[g]["boards"], hb_nn[g, :st_nn[g]]) and np.array_equal(recs_nn[g]["results"], hr_nn[g, :st_nn[g]])
+              for g in range(Gn))
+ok &= same_nn
+if rank == 0:
+    print(f"NN-policy selfplay_batch ({Gn} main games, mcts_nn number=5) sharded over {world} ranks {'ok' if same_nn else 'MISMATCH'} "
+          f"({mv_nn} policy moves, {int(st_nn.sum())} main moves)", flush=True)
 # data-parallel training step: every rank ends with identical parameters
 torch.manual_seed(0)
 st = pkg.trainer.TrainStep(pkg.network.ConvNet(64, 3).cuda().train(), lr=1e-3, max_batch=256)
