@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b2048.h"
@@ -62,6 +63,11 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
     c->k2_variant = 1;
     c->tc_wide = 1;
+    // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
+    // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
+    // line queue behind the slots the one-set kernel is the faster one up to ~7,000 lines in flight.
+    c->main_single_pct = 150;
+    if (const char *e = getenv("B2048_MAIN_SINGLE_PCT")) c->main_single_pct = atoi(e);  // bring-up / A-B runs only
     CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMemset(c->counters, 0, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
@@ -473,7 +479,9 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
             p.single_set = p.n <= (long)(grid / models) * tc::TILE_BOARDS;
         } else {
             // few items: spread them over the SMs, one tile-set per CTA (lower per-step latency)
-            p.single_set = total <= (long)c->num_sms * tc::TILE_BOARDS;
+            long limit = (long)c->num_sms * tc::TILE_BOARDS;
+            if (p.main_mode) limit = limit * c->main_single_pct / 100;
+            p.single_set = total <= limit;
             grid = p.single_set ? grid_for(total, tc::TILE_BOARDS, c->num_sms)
                                 : grid_for(total, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
         }

@@ -18,6 +18,7 @@ struct b2048_ctx {
     uint8_t *moved_fwd, *moved_rev, *legal;
     uint2 *rowstat;
     std::atomic<int> k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide
+    int main_single_pct;          // main-game launches up to this % of (32 x #SMs) lines in flight run one tile-set per CTA
     std::atomic<int> tc_wide;     // 1 = small tensor-core launches use the 16-warp one-set (latency) kernel variant
     unsigned long long *counters;  // N_COUNTERS work cursors, one per in-flight launch
     int *err_flag;                 // [0] spawn on a full board (ValueError in the reference), [1] table self-check

@@ -141,87 +141,151 @@ class TrainStep:
                                                   L.stream_ptr(self.device)))
         self._invalidate_weight_images()
 
-    def step(self, boards, targets):
+    def step(self, boards, targets, group=None):
+        """One optimisation step.  With an initialised process group it is data parallel: every rank runs its own
+        batch, the flat gradient is averaged over the ranks between backward and Adam, and so are the BatchNorm running
+        statistics the kernels updated in place (batch statistics stay per rank, as in DistributedDataParallel without
+        SyncBatchNorm) -- parameters AND buffers stay identical on all ranks."""
         loss = self.forward_backward(boards, targets)
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self.grad)  # data parallel: mean gradient over ranks
-            self.grad /= torch.distributed.get_world_size()
+        td = torch.distributed
+        if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+            ws = td.get_world_size(group)
+            td.all_reduce(self.grad, group=group)
+            td.all_reduce(self.bn, group=group)
+            self.grad /= ws
+            self.bn /= ws
         self.adam()
         return loss
 
 
-def train_epoch(stepper, boards, targets, batch_size, generator=None):
-    """One shuffled pass (DataLoader(shuffle=True), trainer.py:29,55): returns the mean batch loss as a float."""
+def _world(group=None):
+    td = torch.distributed
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(group), td.get_world_size(group)
+    return 0, 1
+
+
+def train_epoch(stepper, boards, targets, batch_size, generator=None, group=None):
+    """One shuffled pass (DataLoader(shuffle=True), trainer.py:29,55): returns (mean batch loss, batches).
+    Data parallel: every rank draws the SAME permutation (pass generators seeded alike, or rely on torch.manual_seed
+    having been called with the same seed on every rank) and takes its own `batch_size` slice of each global batch of
+    world_size * batch_size records, so an epoch still visits every record once."""
+    rank, world = _world(group)
     n = boards.numel()
     perm = torch.randperm(n, device=boards.device, generator=generator)
+    if world > 1:
+        torch.distributed.broadcast(perm, 0, group=group)  # one permutation for all ranks, whatever their RNG state
     total = torch.zeros((), dtype=torch.float32, device=boards.device)
     batches = 0
-    for i in range(0, n, batch_size):
-        idx = perm[i:i + batch_size]
-        if idx.numel() < 2:
-            break
-        total += stepper.step(boards[idx], targets[idx])
+    for i in range(0, n, batch_size * world):
+        idx = perm[i + rank * batch_size:i + (rank + 1) * batch_size]
+        short = torch.tensor([idx.numel() < 2], device=boards.device)
+        if world > 1:
+            torch.distributed.all_reduce(short, op=torch.distributed.ReduceOp.MAX, group=group)
+        if bool(short.item()):
+            break  # a ragged last global batch that leaves some rank without records is dropped on every rank
+        total += stepper.step(boards[idx], targets[idx], group=group)
         batches += 1
     return float(total.item()) / max(batches, 1), batches
 
 
-def main(args):
-    """trainer.py:14-97."""
-    if args.name:
-        args.name += '_'
-    logname = f'{args.name}{args.t_tuple[0]}_{args.t_tuple[1]}_soft{args.soft}' \
-              f'c{args.channels}b{args.blocks}_p{args.patience}_' \
-              f'bs{args.batch_size}lr{args.lr}d{args.decay}_s{args.seed}'
-    print(logname)
-    random.seed(args.seed)
-    np.random.seed(args.seed)
-    torch.manual_seed(args.seed)
+class Patience:
+    """Early stopping of trainer.py:46-52,66-67,81-91: stop after `patience` epochs without a new best evaluation
+    (patience 0: never), and give up at once if the third epoch's mean loss is still above 0.210."""
+
+    def __init__(self, patience, epochs):
+        self.limit = epochs if patience == 0 else patience
+        self.best, self.since_best = 0.0, 0
+
+    def after_train(self, epoch, mean_loss):
+        self.since_best += 1
+        if epoch == 2 and mean_loss > 210 / 1000:
+            self.limit = 0
+
+    def after_eval(self, value):
+        """-> True when `value` is a new best (ties count, trainer.py:81)."""
+        if value >= self.best:
+            self.best, self.since_best = value, 0
+            return True
+        return False
+
+    @property
+    def exhausted(self):
+        return self.since_best >= self.limit
+
+    @property
+    def remaining(self):
+        return self.limit - self.since_best
+
+
+def run_name(args, pretrained):
+    """The reference's log / checkpoint name grammar (trainer.py:17-21,38)."""
+    prefix = (args.name + '_') if args.name else ''
+    name = (f'{prefix}{args.t_tuple[0]}_{args.t_tuple[1]}_soft{args.soft}c{args.channels}b{args.blocks}_p{args.patience}_'
+            f'bs{args.batch_size}lr{args.lr}d{args.decay}_s{args.seed}')
+    return 'pre_' + name if pretrained else name
+
+
+def main(args, group=None):
+    """trainer.py:14-97: train on the self-play records under args.path, evaluate with eval_nn_min after every epoch,
+    keep the best checkpoint, stop on patience; returns (losses, evaluations).  Under torchrun the run is data parallel
+    (see TrainStep.step / train_epoch); only rank 0 prints, evaluates and writes models/ and logs/."""
+    if (args.channels, args.blocks) != (64, 3):
+        raise SystemExit('the B200 kernels implement c64b3 only: use --channels 64 --blocks 3 '
+                         f'(got c{args.channels}b{args.blocks})')
+    rank, world = _world(group)
+    say = print if rank == 0 else (lambda *a, **k: None)
+    logname = run_name(args, bool(args.pretrained))
+    say(logname)
+    for seeder in (random.seed, np.random.seed, torch.manual_seed):
+        seeder(args.seed)
     L.require_cuda()
     device = torch.device('cuda')
-    print('Using {}'.format(device))
+    say('Using {}'.format(device))
 
-    train_set = OneHotConvGameDataset(args.path, args.t_tuple[0], args.t_tuple[1], device, soft=args.soft)
-    m = ConvNet(channels=args.channels, blocks=args.blocks, precision="fp16")
+    records = OneHotConvGameDataset(args.path, args.t_tuple[0], args.t_tuple[1], device, soft=args.soft)
+    net = ConvNet(channels=64, blocks=3, precision="fp16")
     if args.pretrained:
-        m.load_state_dict(torch.load('models/{}.pt'.format(args.pretrained), map_location=device))
-        print('Loaded ' + args.pretrained)
-        logname = 'pre_' + logname
-    m.to(device)
-    stepper = TrainStep(m, lr=args.lr, weight_decay=args.decay, max_batch=args.batch_size,
+        net.load_state_dict(torch.load('models/{}.pt'.format(args.pretrained), map_location=device))
+        say('Loaded ' + args.pretrained)
+    net.to(device)
+    stepper = TrainStep(net, lr=args.lr, weight_decay=args.decay, max_batch=args.batch_size,
                         precision=getattr(args, "precision", "fp32"))
-    t_loss, min_move = [], []
-    best, timer = 0.0, 0
-    stop = args.epochs if args.patience == 0 else args.patience
+    if world > 1:  # same start on every rank (DDP broadcasts parameters and buffers once at construction)
+        torch.distributed.broadcast(stepper.params, 0, group=group)
+        torch.distributed.broadcast(stepper.bn, 0, group=group)
+    patience = Patience(args.patience, args.epochs)
+    losses, evals = [], []
     for epoch in range(args.epochs):
-        print('-' * 10)
-        print('Epoch: {}'.format(epoch))
-        timer += 1
-        m.train()
-        running_loss, _ = train_epoch(stepper, train_set.packed, train_set.results, args.batch_size)
-        if epoch == 2 and running_loss > 210 / 1000:
-            stop = 0
-        print('Train mLoss: {:.3f}'.format(1e3 * running_loss))
-        t_loss.append(running_loss)
+        say('-' * 10)
+        say('Epoch: {}'.format(epoch))
+        net.train()
+        mean_loss, _ = train_epoch(stepper, records.packed, records.results, args.batch_size, group=group)
+        patience.after_train(epoch, mean_loss)
+        say('Train mLoss: {:.3f}'.format(1e3 * mean_loss))
+        losses.append(mean_loss)
 
-        m.eval()
-        time1 = time()
-        ave_min_move = eval_nn_min(m, number=10, repeats=40, device=device)
-        time_str = ', took {:.0f} seconds'.format(time() - time1)
-        min_move.append(ave_min_move)
-        if ave_min_move >= best:
-            print(str(ave_min_move) + ' ** Best' + time_str)
-            best, timer = ave_min_move, 0
-            torch.save(m.state_dict(), 'models/' + logname + '_best.pt')
+        net.eval()
+        started = time()
+        # every rank plays the same evaluation games (same seed, identical weights): the decision below is identical
+        # everywhere without an exchange
+        first_death = eval_nn_min(net, number=10, repeats=40, device=device)
+        took = ', took {:.0f} seconds'.format(time() - started)
+        evals.append(first_death)
+        if patience.after_eval(first_death):
+            say(str(first_death) + ' ** Best' + took)
+            if rank == 0:
+                torch.save(net.state_dict(), 'models/' + logname + '_best.pt')
         else:
-            print(str(ave_min_move) + time_str)
-        if timer >= stop:
-            print('Ran out of patience')
-            print(f'Best score: {best}')
+            say(str(first_death) + took)
+        if patience.exhausted:
+            say('Ran out of patience')
+            say(f'Best score: {patience.best}')
             break
-        else:
-            print(f'{stop - timer} epochs remaining')
-    np.savez('logs/' + logname, t_loss=t_loss, min_move=min_move, params=args)
-    return t_loss, min_move
+        say(f'{patience.remaining} epochs remaining')
+    if rank == 0:
+        np.savez('logs/' + logname, t_loss=losses, min_move=evals, params=args)
+    return losses, evals
 
 
 def parser():

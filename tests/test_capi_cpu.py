@@ -84,3 +84,35 @@ def test_new_entry_points_fail_loudly_without_gpu(built, pkg):
         pkg.analysis.fixed_distribution(8, seed=1)
     with pytest.raises(pkg.B2048Error):
         pkg.evolve.eval_population([m], number=2, seed=1)
+
+
+def test_trainer_host_logic(pkg):
+    # the parts of the training driver that need no GPU: run name grammar (trainer.py:17-21,38), the patience rule
+    # (trainer.py:46-52,66-67,81-91) and the up-front architecture check
+    tr = pkg.trainer
+    args = tr.parser().parse_args(["--name", "x", "--t_tuple", "0", "3400", "--seed", "0"])
+    assert tr.run_name(args, False) == "x_0_3400_soft3.0c64b3_p10_bs2048lr0.1d0.0_s0"
+    assert tr.run_name(tr.parser().parse_args(["--t_tuple", "0", "3400"]), True) == "pre_0_3400_soft3.0c64b3_p10_bs2048lr0.1d0.0_s0"
+    p = tr.Patience(2, 100)
+    p.after_train(0, 0.5)
+    assert p.after_eval(3.0) and not p.exhausted and p.remaining == 2
+    p.after_train(1, 0.4)
+    assert not p.after_eval(2.0) and p.remaining == 1
+    p.after_train(2, 0.3)            # third epoch still above 0.210: give up (trainer.py:66-67)
+    assert p.exhausted
+    q = tr.Patience(0, 7)            # patience 0 = run all epochs
+    for e in range(6):
+        q.after_train(e, 0.1)
+        q.after_eval(0.0 if e else 1.0)
+    assert not q.exhausted and q.remaining == 2
+    with pytest.raises(SystemExit):
+        tr.main(tr.parser().parse_args(["--channels", "16", "--blocks", "5"]))
+    # the self-play command line plays main game N of one fixed session (same record alone or in a batch)
+    assert pkg.selfplay.CLI_GAMES_TOTAL == 1 << 32
+
+
+def test_main_game_workspace_sizes(built, pkg):
+    lib = pkg._lib.load_library()
+    small, big = lib.b2048_selfplay_nn_workspace_bytes(1, 50), lib.b2048_selfplay_nn_workspace_bytes(256, 50)
+    assert 0 < small < big < 4 << 20 and small % 4 == 0
+    assert lib.b2048_selfplay_nn_workspace_bytes(0, 50) == -1 and lib.b2048_selfplay_nn_workspace_bytes(1 << 26, 50) == -1
