@@ -76,10 +76,17 @@ def _to16(x, dtype):
     return t.view(torch.int16).numpy().view(np.uint16), t.to(torch.float32).numpy()
 
 
-def pack_tc(folded, dtype="fp16"):
+SPLIT_LAYERS = (1, 2, 3)  # csrc/convnet_tc.cuh SPLIT_FIRST..SPLIT_LAST
+
+
+def pack_tc(folded, dtype="fp16", precise=False):
     """16-bit tensor-core blob (dtype "fp16" or "bf16"): 21 chunks (layer l, ky) of 192 rows [kx=2 | kx=1 | kx=0] x 64 co, each row
     64 ci fp16 (K-major, pre-swizzled); L0 rows are [W_hi(16 ci) | W_lo(16 ci) | 0]; then the fp32 tail
-    bias[7][64], w7[4][64], b7[4], fcw[4][64], fcb[4]."""
+    bias[7][64], w7[4][64], b7[4], fcw[4][64], fcb[4].
+    precise=True (B2048_PREC_FP16X2_TC, fp16 only): every chunk of layers 1..3 is followed by its lo chunk
+    fp16(W - fp16(W)) -> 30 chunks."""
+    if precise and dtype != "fp16":
+        raise ValueError("the precise tensor-core mode is fp16 hi+lo")
     chunks = []
     for l, w in enumerate(folded["conv_w"]):  # (64 co, cin, 3, 3) float64
         for ky in range(3):
@@ -98,7 +105,24 @@ def pack_tc(folded, dtype="fp16"):
             if not np.isfinite(vals).all():
                 raise ValueError("folded weights overflow " + dtype)
             chunks.append(_swizzle_rows(bits).reshape(-1))
+            if precise and l in SPLIT_LAYERS:
+                lo_rows = np.zeros((TC_CHUNK_ROWS, 64), np.float64)
+                for blk, kx in enumerate((2, 1, 0)):
+                    lo_rows[blk * 64:(blk + 1) * 64, :] = w[:, :, ky, kx] - vals[blk * 64:(blk + 1) * 64, :].astype(np.float64)
+                lo_bits, _ = _to16(lo_rows.astype(np.float32), dtype)
+                chunks.append(_swizzle_rows(lo_bits).reshape(-1))
     wbytes = np.concatenate(chunks).view(np.uint8)
     tail = np.concatenate([np.stack(folded["conv_b"]).reshape(-1), folded["head_w"].reshape(-1), folded["head_b"],
                            folded["fc_w"].reshape(-1), folded["fc_b"]]).astype(np.float32)
     return torch.from_numpy(np.concatenate([wbytes, tail.view(np.uint8)]).copy())
+
+
+def pack_blob(folded, precision):
+    """Weight image for a precision name of network.PRECISIONS."""
+    if precision == "fp32":
+        return pack_fp32(folded)
+    if precision == "fp16x2":
+        return pack_tc(folded, "fp16", precise=True)
+    if precision in ("fp16", "bf16"):
+        return pack_tc(folded, precision)
+    raise ValueError("unknown precision " + repr(precision))

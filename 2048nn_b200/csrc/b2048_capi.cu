@@ -65,8 +65,8 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     c->tc_wide = 1;
     // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
     // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
-    // line queue behind the slots the one-set kernel is the faster one up to ~7,000 lines in flight.
-    c->main_single_pct = 150;
+    // line queue behind the slots the one-set kernel is the faster one up to ~10,000 lines in flight (profiles/r02_main_single_pct.txt).
+    c->main_single_pct = 250;
     if (const char *e = getenv("B2048_MAIN_SINGLE_PCT")) c->main_single_pct = atoi(e);  // bring-up / A-B runs only
     CK(cudaMalloc(&c->counters, N_COUNTERS * sizeof(unsigned long long)));
     CK(cudaMemset(c->counters, 0, N_COUNTERS * sizeof(unsigned long long)));
@@ -97,6 +97,12 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
@@ -395,11 +401,12 @@ extern "C" int b2048_selfplay_fixed(b2048_ctx *c, const uint64_t *starts, int64_
 extern "C" int64_t b2048_convnet_blob_bytes(int precision) {
     if (precision == B2048_PREC_FP32) return (int64_t)CN_FP32_FLOATS * 4;
     if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC) return (int64_t)tc::BLOB_BYTES;
+    if (precision == B2048_PREC_FP16X2_TC) return (int64_t)tc::BLOB_BYTES_PRECISE;
     return -1;
 }
 
 static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boards, float *out_logp, float *out_logits,
-                             float *dbg, int dbg_layer, int64_t n, cudaStream_t st, bool bf16 = false) {
+                             float *dbg, int dbg_layer, int64_t n, cudaStream_t st, bool bf16 = false, bool precise = false) {
     tc::FwdWork::Params p;
     p.boards = (const unsigned long long *)boards;
     p.out_logp = out_logp;
@@ -408,6 +415,13 @@ static int launch_tc_forward(b2048_ctx *c, const void *blob, const uint64_t *boa
     p.counter = take_counters(c, 1);
     CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), st));
     int grid = grid_for(n, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
+    if (precise) {  // one tile-set per CTA whatever the batch size
+        grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
+        tc::tc_persistent_kernel<tc::FwdWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+            p, (const uint8_t *)blob, nullptr, -1, (long)n);
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (!dbg && !bf16 && c->tc_wide.load() && n <= (int64_t)c->num_sms * tc::TILE_BOARDS) {
         // latency mode: at most one 32-board tile per SM -> one tile-set per CTA, all 16 worker warps on its epilogue
         grid = grid_for(n, tc::TILE_BOARDS, c->num_sms);
@@ -442,8 +456,9 @@ extern "C" int b2048_convnet_forward(b2048_ctx *c, int precision, const void *bl
         CK(cudaGetLastError());
         return 0;
     }
-    if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC)
-        return launch_tc_forward(c, blob, boards, out_logp, nullptr, nullptr, -1, n, st, precision == B2048_PREC_BF16_TC);
+    if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC || precision == B2048_PREC_FP16X2_TC)
+        return launch_tc_forward(c, blob, boards, out_logp, nullptr, nullptr, -1, n, st, precision == B2048_PREC_BF16_TC,
+                                 precision == B2048_PREC_FP16X2_TC);
     return fail_msg("b2048_convnet_forward: unknown precision");
 }
 
@@ -471,6 +486,19 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         CK(cudaGetLastError());
         return 0;
     }
+    if (precision == B2048_PREC_FP16X2_TC) {
+        if (models > 1) return fail_msg("b2048 NN playout: the precise tensor-core mode plays one model per launch");
+        p.single_set = 1;
+        const int grid = grid_for(total, tc::TILE_BOARDS, c->num_sms);
+        if (p.main_mode)
+            tc::tc_persistent_kernel<MainWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        else
+            tc::tc_persistent_kernel<PlayWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (precision == B2048_PREC_FP16_TC || precision == B2048_PREC_BF16_TC) {
         int grid;
         if (models > 1) {
@@ -487,7 +515,7 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         }
         const bool wide = p.single_set && models == 1 && precision == B2048_PREC_FP16_TC && c->tc_wide.load();
         if (p.main_mode) {
-            if (precision != B2048_PREC_FP16_TC) return fail_msg("b2048_selfplay_nn: precision must be FP32 or FP16_TC");
+            if (precision != B2048_PREC_FP16_TC) return fail_msg("b2048_selfplay_nn: precision must be FP32, FP16_TC or FP16X2_TC");
             if (wide)
                 tc::tc_persistent_kernel<MainWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                     p, (const uint8_t *)p.blob, nullptr, -1, 0);

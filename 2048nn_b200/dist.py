@@ -36,6 +36,14 @@ def shard_lines(number, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_games(G, rank, world_size):
+    """Device-resident main games (selfplay_batch) shard by game id: rank r plays games [g0, g0 + n) of the session;
+    every rank's share is padded to `per` games when the records are gathered.  -> (g0, n, per)"""
+    per = (int(G) + int(world_size) - 1) // int(world_size)
+    g0 = min(int(G), int(rank) * per)
+    return g0, max(0, min(int(G), g0 + per) - g0), per
+
+
 REPLICATE_BELOW_LINES = 148 * 32  # one 32-board tile-set per SM: a root evaluation this small is latency-bound
 
 

@@ -158,7 +158,7 @@ def mcts_fixed_lines(origins, number, seed, eval_id_base=0, line_begin=0, line_e
     return r
 
 
-PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2, "fp16x2": 3}
 
 
 def playout_nn(blob, precision, n, seed, gid_base=0, start=None, spawn0=0, group_size=0, device="cuda", want_final=True):

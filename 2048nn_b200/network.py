@@ -8,6 +8,8 @@ and returns `(N,4)` log-probabilities computed by the CUDA kernels (b2048_convne
 
 precision: "fp32" = exact mode (CUDA-core FMA, |dlogp| ~1e-5 vs PyTorch);
            "fp16" = tcgen05 tensor-core mode (fp16 operands, fp32 accumulation);
+           "fp16x2" = precise tensor-core mode (layers L1..L3 with fp16 hi+lo weights and activations: every board
+                    within 1e-2 of the fp32 reference, ~half the throughput of "fp16");
            "bf16" = the same kernels with bf16 operands (fails the 99.9 % argmax bar on the shipped
                     weights; kept so the choice of fp16 is a measurement, not an assumption).
 Training (autograd through forward) is outside this path and raises.
@@ -18,7 +20,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import convnet as _cn
 
-PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2, "fp16x2": 3}
 
 
 class ConvNet(nn.Module):
@@ -54,10 +56,7 @@ class ConvNet(nn.Module):
         key = (precision, self._state_version())
         if self._blob_key != key:
             folded = _cn.fold_state_dict(self.state_dict())
-            if precision == "fp32":
-                b = _cn.pack_fp32(folded)
-            else:
-                b = _cn.pack_tc(folded, precision)
+            b = _cn.pack_blob(folded, precision)
             dev = next(self.parameters()).device
             dev = dev if dev.type == "cuda" else torch.device("cuda")
             self._blob, self._blob_key = b.to(dev), key
@@ -99,7 +98,7 @@ def blob_for(model, precision=None):
     key = (precision, tuple((p.data_ptr(), p._version) for p in model.state_dict().values()))
     if cache.get("key") != key:
         folded = _cn.fold_state_dict(model.state_dict())
-        b = _cn.pack_fp32(folded) if precision == "fp32" else _cn.pack_tc(folded, precision)
+        b = _cn.pack_blob(folded, precision)
         L.require_cuda()
         cache["key"], cache["blob"] = key, b.cuda()
     return cache["blob"], precision

@@ -65,9 +65,7 @@ def _device_games(launch, G, starts, max_steps, first_budget, group):
     dev = torch.device("cuda")
     world = td.get_world_size(group) if td.is_available() and td.is_initialized() else 1
     rank = td.get_rank(group) if world > 1 else 0
-    per = (G + world - 1) // world
-    g0 = min(G, rank * per)
-    n_local = max(0, min(G, g0 + per) - g0)
+    g0, n_local, per = _dist.shard_games(G, rank, world)
     budget = int(min(max_steps, first_budget))
     while True:
         r = None

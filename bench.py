@@ -237,9 +237,7 @@ def main_games_block(pkg, blob, G_total, number, main_steps, steps, warmup, seed
     import torch
 
     eng = pkg.engine
-    per = (G_total + world - 1) // world
-    g0 = min(G_total, rank * per)
-    n_local = max(0, min(G_total, g0 + per) - g0)
+    g0, n_local, _ = importlib.import_module("2048nn_b200.dist").shard_games(G_total, rank, world)
     lc = pkg._lib.launch_count
 
     def play(seed, starts=None):
@@ -369,6 +367,29 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     f1.record()
     torch.cuda.synchronize()
     fwd_boards_per_s = 3 * nb / (f0.elapsed_time(f1) * 1e-3)
+    # the precise tensor-core mode (fp16 hi+lo operands on L1..L3: every board within 1e-2): its cost, same workloads
+    for _ in range(2):
+        m.forward_boards(fb, precision="fp16x2")
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        m.forward_boards(fb, precision="fp16x2")
+    p1.record()
+    torch.cuda.synchronize()
+    blob2 = m.blob("fp16x2")
+    org1 = origins[:args.nn_origins].contiguous()
+    eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 400, 0)
+    torch.cuda.synchronize()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    rp = eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 401, 0)
+    q1.record()
+    torch.cuda.synchronize()
+    precise = {"forward_boards_per_s_per_gpu": 3 * nb / (p0.elapsed_time(p1) * 1e-3),
+               "nn_policy_moves_per_s_per_gpu": float(rp["total_moves"].item()) / (q0.elapsed_time(q1) * 1e-3),
+               "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC): max |dlogp| < 1e-2 on all 150,371 fixture boards "
+                       "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block, one GPU"}
     import copy
     torch_base = torch_forward_baselines(pkg, copy.deepcopy(m), fb) if rank == 0 else None
     # config 3 (one main game, mcts_nn number=50 per main move) and config 4 (256 main games in total, sharded)
@@ -376,7 +397,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     game1 = main_games_block(pkg, blob, 1, number, args.game_steps, args.steps, args.warmup, 5000, 0, 1, barrier)
     sp256 = main_games_block(pkg, blob, args.sp_games, number, args.sp_steps, args.steps, args.warmup, 7000, rank, world, barrier)
     return {"ms": ms, "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "e2e_moves": float(e2e_moves.item()),
-            "fwd_boards_per_s": fwd_boards_per_s, "torch_base": torch_base, "launches": launches,
+            "fwd_boards_per_s": fwd_boards_per_s, "torch_base": torch_base, "launches": launches, "precise": precise,
             "h2d": G * 8, "d2h": G * 4 * 8, "weights": weights, "game1": game1, "sp256": sp256,
             "workload": f"mcts_nn: {G} origins (fresh boards) x 4 root moves x {number} c64b3 policy lines per step over "
                         f"{world} GPU(s): {how}, [G,4] MIN allreduce per step"}
@@ -572,9 +593,11 @@ def main():
     achieved = per_gpu_moves_per_s * INSTR_PER_MOVE
     hbm_bytes = 24.0 * n * args.steps  # 8 B start + 16 B results per game
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same size only)
-    tpath = os.path.join(ROOT, "profiles", "r01_k2_traffic_16m.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_k2_traffic_16m.json")
+    measured_instr = None
     if os.path.exists(tpath):
         tinfo = json.load(open(tpath))
+        measured_instr = tinfo.get("thread_instr_per_move")
         if tinfo.get("games") == n:
             traffic = tinfo["traffic_bytes_per_launch"]
     line = {
@@ -590,9 +613,11 @@ def main():
         "gpu_launches": main_launches,
         "roofline": {"bound": "sm_issue", "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
                      "frac": achieved / issue_peak, "traffic": traffic,
-                     "traffic_source": "committed ncu capture profiles/r01_k2_traffic_16m.json (same size), not measured in this run",
-                     "note": "algorithmic 250 thread-instr/move x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); "
-                             "the kernel is integer-issue bound, HBM sees only %.1f GB/s of %.0f"
+                     "traffic_source": "committed ncu capture profiles/r02_k2_traffic_16m.json (same size), not measured in this run",
+                     "measured_thread_instr_per_move": measured_instr,
+                     "note": "algorithmic 250 thread-instr/move (SURVEY 8d) x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); the kernel "
+                             "EXECUTES 174 thread-instr/move (ncu), 62 %% of them on the half-rate ALU pipe (88 %% busy, the binder; "
+                             "shared-memory wavefronts 86 %%); HBM sees only %.1f GB/s of %.0f"
                              % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
                                 peaks["hbm_gbs"])},
     }
@@ -601,7 +626,7 @@ def main():
         tf = nn_value / world * 5128704.0 / 1e12     # valid-tap FLOP per evaluation, one GPU
         peak_tf = peaks["bf16_tflops_sustained"]
         nn_traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload (1 GPU, default sizes)
-        npath = os.path.join(ROOT, "profiles", "r01_k4_traffic_nn_block.json")
+        npath = os.path.join(ROOT, "profiles", "r02_k4_traffic_nn_block.json")
         if os.path.exists(npath) and args.nn_origins == 256 and args.nn_lines == 50:
             nn_traffic = json.load(open(npath))["traffic_bytes_per_launch"]
         fwd_tf = nn["fwd_boards_per_s"] * 5128704.0 / 1e12
@@ -622,9 +647,10 @@ def main():
                     "h2d_bytes_per_step": nn["h2d"], "d2h_bytes_per_step": nn["d2h"]},
             "gpu_launches": nn["launches"],
             "forward_only": forward_only,
+            "precise_mode": nn["precise"],
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": nn_traffic,
-                         "traffic_source": "committed ncu capture profiles/r01_k4_traffic_nn_block.json (default sizes), not measured in this run",
+                         "traffic_source": "committed ncu capture profiles/r02_k4_traffic_nn_block.json (default sizes), not measured in this run",
                          "note": "5,128,704 valid-tap FLOP per policy evaluation x evals/s on one GPU vs the %s "
                                  "sustained dense bf16/fp16 GEMM peak; the kernel executes 1.25x that (y-padding rows, K-doubled L0)"
                                  % peak_kind},

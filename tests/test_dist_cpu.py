@@ -123,3 +123,16 @@ def test_shard_plan():
     for G, ws in ((8, 8), (9, 4), (2048, 8)):
         parts = [d.shard_plan(G, 10, r, ws) for r in range(ws)]
         assert parts[0][0] == 0 and parts[-1][1] == G and all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+
+
+def test_shard_games_partition():
+    d = importlib.import_module("2048nn_b200.dist")
+    for G, ws in ((256, 8), (256, 1), (5, 2), (3, 8), (1, 4), (17, 4)):
+        parts = [d.shard_games(G, r, ws) for r in range(ws)]
+        covered = []
+        for g0, n, per in parts:
+            assert per == parts[0][2] and 0 <= n <= per
+            covered += list(range(g0, g0 + n))
+        assert covered == list(range(G))            # disjoint, ordered, complete
+        assert ws * parts[0][2] >= G                # the gather buffer of `per` games per rank holds every record
+    assert d.shard_games(256, 3, 8) == (96, 32, 32)  # BASELINE config 4 on 8 GPUs: 32 main games = 6,400 lines per GPU
