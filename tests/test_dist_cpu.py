@@ -136,3 +136,47 @@ def test_shard_games_partition():
         assert covered == list(range(G))            # disjoint, ordered, complete
         assert ws * parts[0][2] >= G                # the gather buffer of `per` games per rank holds every record
     assert d.shard_games(256, 3, 8) == (96, 32, 32)  # BASELINE config 4 on 8 GPUs: 32 main games = 6,400 lines per GPU
+
+
+def _epoch_worker(rank, world_size, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    tr = importlib.import_module("2048nn_b200.trainer")
+
+    class Recorder:  # stands in for TrainStep (the CUDA step needs a GPU): remembers which records it was given
+        def __init__(self):
+            self.seen = []
+
+        def step(self, boards, targets, group=None):
+            self.seen.append(boards.clone())
+            return torch.tensor(float(boards.numel()))
+
+    torch.manual_seed(100 + rank)  # ranks with DIFFERENT generator states must still use one permutation
+    n, bs = 53, 8
+    boards = torch.arange(n, dtype=torch.int64)
+    rec = Recorder()
+    mean_loss, batches = tr.train_epoch(rec, boards, torch.zeros(n, 4), bs)
+    q.put((rank, batches, mean_loss, torch.cat(rec.seen).tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_epoch_world2():
+    # trainer.train_epoch under a process group: one permutation for all ranks, disjoint slices of every global batch,
+    # a ragged last global batch that leaves a rank short is dropped on every rank (same number of steps everywhere)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_epoch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, b0, l0, s0), (_, b1, l1, s1) = got
+    assert b0 == b1 == 3                      # 53 records, global batch 16: 3 full global batches, the ragged rest dropped
+    assert len(s0) == len(s1) == 24 and not set(s0) & set(s1) and len(set(s0) | set(s1)) == 48
+    assert l0 == l1 == 8.0
