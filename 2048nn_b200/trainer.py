@@ -143,19 +143,26 @@ class TrainStep:
 
     def step(self, boards, targets, group=None):
         """One optimisation step.  With an initialised process group it is data parallel: every rank runs its own
-        batch, the flat gradient is averaged over the ranks between backward and Adam, and so are the BatchNorm running
-        statistics the kernels updated in place (batch statistics stay per rank, as in DistributedDataParallel without
-        SyncBatchNorm) -- parameters AND buffers stay identical on all ranks."""
+        batch and the flat gradient is averaged over the ranks between backward and Adam (one allreduce), so the
+        parameters stay identical on all ranks.  BatchNorm batch statistics stay per rank, as in
+        DistributedDataParallel without SyncBatchNorm; the running statistics are averaged by sync_buffers()."""
         loss = self.forward_backward(boards, targets)
         td = torch.distributed
         if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
-            ws = td.get_world_size(group)
             td.all_reduce(self.grad, group=group)
-            td.all_reduce(self.bn, group=group)
-            self.grad /= ws
-            self.bn /= ws
+            self.grad /= td.get_world_size(group)
         self.adam()
         return loss
+
+    def sync_buffers(self, group=None):
+        """Average the BatchNorm running statistics over the ranks.  The running-statistics update is linear in
+        (running value, batch statistic), so averaging once -- before an evaluation or a checkpoint -- gives exactly
+        the buffers that averaging after every step would: no per-step collective is needed for them."""
+        td = torch.distributed
+        if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+            td.all_reduce(self.bn, group=group)
+            self.bn /= td.get_world_size(group)
+            self._invalidate_weight_images()
 
 
 def _world(group=None):
@@ -261,6 +268,7 @@ def main(args, group=None):
         say('Epoch: {}'.format(epoch))
         net.train()
         mean_loss, _ = train_epoch(stepper, records.packed, records.results, args.batch_size, group=group)
+        stepper.sync_buffers(group)  # identical BatchNorm buffers on every rank before evaluating / saving
         patience.after_train(epoch, mean_loss)
         say('Train mLoss: {:.3f}'.format(1e3 * mean_loss))
         losses.append(mean_loss)

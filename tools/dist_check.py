@@ -56,12 +56,14 @@ g = torch.Generator(device="cuda").manual_seed(100 + rank)
 for _ in range(3):
     b = torch.randint(0, 2 ** 62, (256,), generator=g, device="cuda", dtype=torch.int64) & 0x7777777777777777
     st.step(b, torch.softmax(torch.randn(256, 4, generator=g, device="cuda"), 1))
-ref = st.params.clone()
+st.sync_buffers()
+ref, refb = st.params.clone(), st.bn.clone()
 dist.broadcast(ref, 0)
-same_tr = torch.equal(ref, st.params)
+dist.broadcast(refb, 0)
+same_tr = torch.equal(ref, st.params) and torch.equal(refb, st.bn)
 ok &= same_tr
 if rank == 0:
-    print(f"data-parallel TrainStep: parameters identical on all ranks: {same_tr}", flush=True)
+    print(f"data-parallel TrainStep: parameters and BatchNorm buffers identical on all ranks: {same_tr}", flush=True)
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()
