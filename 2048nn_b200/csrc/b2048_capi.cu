@@ -62,7 +62,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->legal, 65536));
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
     c->k2_variant = 1;
-    c->tc_wide = 1;
+    c->tc_wide = 2;
     // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
     // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
     // line queue behind the slots the one-set kernel is the faster one up to ~10,000 lines in flight (profiles/r02_main_single_pct.txt).
@@ -98,6 +98,10 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpecWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpecWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -132,8 +136,9 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
 extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
 extern "C" int64_t b2048_launch_count(const b2048_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
 
-extern "C" int b2048_set_latency_mode(b2048_ctx *c, int on) {
-    c->tc_wide.store(on ? 1 : 0);
+extern "C" int b2048_set_latency_mode(b2048_ctx *c, int mode) {
+    if (mode < 0 || mode > 2) return fail_msg("b2048_set_latency_mode: mode must be 0, 1 or 2");
+    c->tc_wide.store(mode);
     return 0;
 }
 
@@ -513,7 +518,20 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
             grid = p.single_set ? grid_for(total, tc::TILE_BOARDS, c->num_sms)
                                 : grid_for(total, tc::TILE_BOARDS * tc::NSETS, c->num_sms);
         }
-        const bool wide = p.single_set && models == 1 && precision == B2048_PREC_FP16_TC && c->tc_wide.load();
+        const int lat = c->tc_wide.load();
+        const bool wide = p.single_set && models == 1 && precision == B2048_PREC_FP16_TC && lat >= 1;
+        if (wide && lat >= 2 && total <= (long)c->num_sms * SPEC_LINES) {
+            // latency regime (config 3: 200 lines): two-ply speculation, 6 lines x 5 slots per tile, one tile per CTA
+            grid = grid_for(total, SPEC_LINES, c->num_sms);
+            if (p.main_mode)
+                tc::tc_persistent_kernel<MainSpecWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<PlaySpecWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            CK(cudaGetLastError());
+            return 0;
+        }
         if (p.main_mode) {
             if (precision != B2048_PREC_FP16_TC) return fail_msg("b2048_selfplay_nn: precision must be FP32, FP16_TC or FP16X2_TC");
             if (wide)

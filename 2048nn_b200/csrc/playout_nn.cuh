@@ -495,60 +495,168 @@ __global__ void __launch_bounds__(512) playout_nn_fp32_kernel(const NNPlayParams
 // of each worker group's owner warp: consume the forward's logits (move choice, spawn, death), refill
 // from the global work counter, hand the next 32 boards to the network.  The engine phase of one set
 // overlaps the other set's forward.
+// Candidate moves of `board` whose next spawn is draw number `draw_idx` of stream `key` (see SlotCand).
+__device__ __forceinline__ void fill_cand(const NNPlayParams &p, SlotCand *c, u64 board, u64 key, u32 draw_idx, int gmin) {
+    const u64 draw = rng_draw(key, B2048_INIT_DRAWS + p.spawn0 + draw_idx);
+    u32 legal = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        u32 s;
+        u64 f = move_exact(board, d, p.tb, s);
+        if (f != board) {
+            legal |= 1u << d;
+            if (countzero(f) == 0) {
+                legal |= 1u << (8 + d);
+            } else {
+                u32 four;
+                f = spawn_tile(f, draw, four);
+            }
+        }
+        c->next[d] = f;
+        c->score[d] = s;
+    }
+    c->legal = legal;
+    c->gmin = gmin;
+}
+
+// highest logit among the legal directions (ties -> lower index, as the stable descending argsort); -1: no legal move
+__device__ __forceinline__ int best_legal(const float *z, u32 legal) {
+    int best = -1;
+    float bz = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+        if (((legal >> d) & 1u) && (best < 0 || z[d] > bz)) best = d, bz = z[d];
+    return best;
+}
+
+// Two-ply speculation (latency regime: far fewer lines than game slots, e.g. BASELINE config 3 = 200 lines on a GPU with
+// 4,736 slots).  A line owns SPEC_GROUP = 5 consecutive slots of a tile: its current board and the four boards that follow from
+// it (move d + the spawn that is already determined by the line's stream).  One forward evaluates all five, so after it the line
+// makes its move AND the move of the board it arrives at: two policy moves per forward, i.e. half the dependent forwards per
+// line, for 5x the (otherwise idle) tensor work.  The boards evaluated are the boards the one-ply kernel would evaluate and a
+// board's logits do not depend on its slot, so the moves -- and every result -- are identical.
+constexpr int SPEC_GROUP = 5, SPEC_LINES = 6;  // 6 lines x 5 slots = 30 of a tile's 32 slots
+__device__ __forceinline__ void nn_move_spec(const NNPlayParams &p, GameSlot &g, const float *logits, const SlotCand *cands,
+                                             int lead, u32 &moves_done) {
+    const SlotCand &c0 = cands[lead];
+    if (g.group >= 0 && (int)g.count >= c0.gmin) {
+        nn_finish(p, g);
+        return;
+    }
+    const int b0 = best_legal(logits + 4 * lead, c0.legal);
+    if (b0 < 0) {
+        nn_finish(p, g);
+        return;
+    }
+    if ((c0.legal >> (8 + b0)) & 1u) {
+        *p.err_flag = 1;
+        nn_finish(p, g);
+        return;
+    }
+    g.board = c0.next[b0];
+    g.score += c0.score[b0];
+    g.count++;
+    moves_done++;
+    // second ply: the board just reached is the one slot lead + 1 + b0 evaluated in the same forward
+    if (g.group >= 0 && (int)g.count >= c0.gmin) {
+        nn_finish(p, g);
+        return;
+    }
+    const int cl = lead + 1 + b0;
+    const SlotCand &c1 = cands[cl];
+    const int b1 = best_legal(logits + 4 * cl, c1.legal);
+    if (b1 < 0) {
+        nn_finish(p, g);
+        return;
+    }
+    if ((c1.legal >> (8 + b1)) & 1u) {
+        *p.err_flag = 1;
+        nn_finish(p, g);
+        return;
+    }
+    g.board = c1.next[b1];
+    g.score += c1.score[b1];
+    g.count++;
+    moves_done++;
+}
+
 // MAIN = true: the device-resident main-game mode (slots are fed by the line queue, mg_service), a separate kernel
-// instantiation so that the plain playout kernel carries none of its code.
-template <bool MAIN>
+// instantiation so that the plain playout kernel carries none of its code.  SPEC = true: two-ply speculation (above).
+template <bool MAIN, bool SPEC = false>
 struct PlayWorkT {
     typedef NNPlayParams Params;
     struct State {
         GameSlot g;
         u32 moves_done;
         bool queue_empty;
+        // SPEC: the board this slot evaluates (a line's current board or one of its four successors), its stream and the
+        // index of the spawn that follows a move from it
+        u64 my_board, my_key;
+        u32 my_draw;
     };
     __device__ static size_t blob_offset(const Params &p) {
         return p.n_models > 1 ? (size_t)(blockIdx.x % (unsigned)p.n_models) * (size_t)p.blob_stride : 0;
     }
+    __device__ static bool is_leader(int lane) { return !SPEC || (lane < SPEC_GROUP * SPEC_LINES && lane % SPEC_GROUP == 0); }
     __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
         st.g.closing = 0;
         st.g.slot = 0;
         st.g.board = 0;
+        st.g.key = 0;
+        st.g.count = 0;
+        st.g.group = -1;
         st.moves_done = 0;
+        st.my_board = 0, st.my_key = 0, st.my_draw = 0;
         // latency mode (few work items): one tile-set per CTA so a step is not interleaved with a second set
         st.queue_empty = (set > 0) && p.single_set;
+        if (SPEC && !is_leader((int)(threadIdx.x & 31))) st.queue_empty = true;  // successor slots never take work items
     }
     __device__ static void prefetch(const Params &p, State &st, uint8_t *scratch, int lane) {
-        if (!st.g.live) return;
         SlotCand *c = reinterpret_cast<SlotCand *>(scratch) + lane;
-        const u64 draw = rng_draw(st.g.key, B2048_INIT_DRAWS + p.spawn0 + st.g.count);  // this move's spawn
-        u32 legal = 0;
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            u32 s;
-            u64 f = move_exact(st.g.board, d, p.tb, s);
-            if (f != st.g.board) {
-                legal |= 1u << d;
-                if (countzero(f) == 0) {
-                    legal |= 1u << (8 + d);
-                } else {
-                    u32 four;
-                    f = spawn_tile(f, draw, four);
-                }
-            }
-            c->next[d] = f;
-            c->score[d] = s;
+        if (SPEC) {
+            if (!st.my_board) return;
+            const bool lead = is_leader(lane);
+            fill_cand(p, c, st.my_board, st.my_key, st.my_draw,
+                      (lead && st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff);
+            return;
         }
-        c->legal = legal;
-        c->gmin = (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff;
+        if (!st.g.live) return;
+        fill_cand(p, c, st.g.board, st.g.key, st.g.count,
+                  (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff);
     }
     __device__ static int step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
                                int lane, long &dbg_base, uint8_t *scratch) {
         dbg_base = 0;
-        if (!first && st.g.live)
-            nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
-        if (MAIN) mg_service(p, st.g, true, st.queue_empty, lane, false);
-        else if (!st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
-        s_boards[lane] = st.g.live ? st.g.board : 0ULL;
+        const bool lead = is_leader(lane);
+        if (!first && st.g.live) {
+            if (SPEC) nn_move_spec(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.moves_done);
+            else nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
+        }
+        if (MAIN) mg_service(p, st.g, lead, st.queue_empty, lane, false);
+        else if (lead && !st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
+        if (SPEC) {
+            // the line's leader hands its board / stream / move count to its four successor slots
+            const int sub = lane % SPEC_GROUP, src = (lane < SPEC_GROUP * SPEC_LINES) ? lane - sub : 0;
+            const u64 lb = __shfl_sync(0xffffffffu, st.g.board, src), lk = __shfl_sync(0xffffffffu, st.g.key, src);
+            const u32 lc = __shfl_sync(0xffffffffu, st.g.count, src);
+            const int ll = __shfl_sync(0xffffffffu, st.g.live, src);
+            u64 mine = 0;
+            if (lead) {
+                mine = st.g.live ? st.g.board : 0ULL;
+            } else if (lane < SPEC_GROUP * SPEC_LINES && ll) {
+                u32 sc;
+                const u64 f = move_exact(lb, sub - 1, p.tb, sc);
+                if (f != lb && countzero(f) != 0) {
+                    u32 four;
+                    mine = spawn_tile(f, rng_draw(lk, B2048_INIT_DRAWS + p.spawn0 + lc), four);  // == SlotCand.next[sub - 1] of the leader
+                }
+            }
+            st.my_board = mine, st.my_key = lk, st.my_draw = lead ? lc : lc + 1u;
+            s_boards[lane] = mine;
+        } else {
+            s_boards[lane] = st.g.live ? st.g.board : 0ULL;
+        }
         const unsigned any = __ballot_sync(0xffffffffu, st.g.live);
         if (MAIN && !any && __ballot_sync(0xffffffffu, !st.queue_empty))
             return tc::RUN_IDLE;  // no line here now, main games still running: lines may be queued any moment
@@ -562,5 +670,7 @@ struct PlayWorkT {
 };
 typedef PlayWorkT<false> PlayWork;
 typedef PlayWorkT<true> MainWork;
+typedef PlayWorkT<false, true> PlaySpecWork;
+typedef PlayWorkT<true, true> MainSpecWork;
 
 }  // namespace b2048

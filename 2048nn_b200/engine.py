@@ -282,9 +282,10 @@ def set_playout_variant(variant, device=None):
     L.check(L.load_library().b2048_set_playout_variant(L.ctx(device), int(variant)))
 
 
-def set_latency_mode(on, device=None):
-    """Small tensor-core launches: 16-warp one-set kernel variant on (default) / off (b2048_set_latency_mode)."""
-    L.check(L.load_library().b2048_set_latency_mode(L.ctx(device), int(bool(on))))
+def set_latency_mode(mode, device=None):
+    """Small tensor-core launches (b2048_set_latency_mode): 0 = no latency variant, 1 = 16-warp one-set kernel,
+    2 (default) = + two-ply speculation for launches with few lines.  Results are identical in every mode."""
+    L.check(L.load_library().b2048_set_latency_mode(L.ctx(device), int(mode)))
 
 
 def num_sms(device=None):

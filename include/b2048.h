@@ -69,10 +69,15 @@ int64_t b2048_launch_count(const b2048_ctx *ctx);
  * move; 0 = the L,U,D,R attempt cascade.  Both are bit-exact; the switch exists for A/B measurements. */
 int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
 
-/* Tensor-core launches small enough for one 32-board tile per SM (forward of <= 32 x #SMs boards, root evaluations /
- * main games with <= 32 x #SMs lines) run a latency variant of the kernel: one tile-set per CTA with all 16 worker warps
- * on its epilogue.  on = 0 switches it off (A/B measurements; results are identical either way).  Default: on. */
-int b2048_set_latency_mode(b2048_ctx *ctx, int on);
+/* Latency variants of the tensor-core kernels for small launches (results are identical in every mode):
+ *   mode 1  launches with at most one 32-board tile per SM (forward of <= 32 x #SMs boards, root evaluations / main games
+ *           with <= 32 x #SMs lines; main games up to 2.5x that) run one tile-set per CTA with all 16 worker warps on its
+ *           epilogue;
+ *   mode 2  (default) additionally, playouts with at most 6 x #SMs lines in flight (BASELINE config 3: 200 lines) run with
+ *           two-ply speculation: a line's current board and its four successors are evaluated in one forward, so every
+ *           forward advances the line by two policy moves (half the dependent forwards per mcts_nn call);
+ *   mode 0  both off (A/B measurements). */
+int b2048_set_latency_mode(b2048_ctx *ctx, int mode);
 
 /* Device error flag: set when a spawn met countzero == 0 (the reference raises ValueError from
  * randrange(0), board.py:87).  Reads and clears it into *out_host; synchronises `stream`. */

@@ -126,3 +126,36 @@ def test_context_of_another_gpu_from_one_process(pkg):
     r1 = pkg.engine.mcts_fixed_lines(o1, 5, 3, 0)
     r0 = pkg.engine.mcts_fixed_lines(o1.to("cuda:0"), 5, 3, 0)
     assert torch.equal(r1["lmoves"].cpu(), r0["lmoves"].cpu()) and torch.cuda.current_device() == 0
+
+
+def test_latency_modes_give_identical_results(pkg, net, ng):
+    # mode 0: two tile-sets / 8-warp groups only; 1: 16-warp one-set kernel for small launches; 2: + two-ply speculation
+    # (a line's board and its four successors in one forward).  Same boards evaluated, same logits, same moves: every
+    # result must be bit-identical.  Sizes chosen so that mode 2 really speculates (<= 6 x #SMs lines in flight).
+    eng = pkg.engine
+    blob = net.blob("fp16")
+    origins = eng.init_boards(3, 9, 0)
+    boards = torch.from_numpy(ng["lg_boards"][:1000].view(np.int64).copy()).cuda()
+    ref = None
+    try:
+        for mode in (0, 1, 2):
+            eng.set_latency_mode(mode)
+            r = eng.mcts_nn_lines(blob, "fp16", origins, 20, 77, 5, per_line=False)
+            g = eng.playout_nn(blob, "fp16", 100, 78, 0)
+            grp = eng.playout_nn(blob, "fp16", 120, 79, 0, group_size=30)
+            sp = eng.selfplay_nn_games(blob, "fp16", 2, 10, 80, max_steps=2048)
+            fw = net.forward_boards(boards, precision="fp16")
+            torch.cuda.synchronize()
+            n0, n1 = int(sp["steps"][0]), int(sp["steps"][1])
+            got = [r["minmov"], g["final"], g["score"], g["moves"], grp["group_min"], sp["final"], sp["score"], sp["steps"],
+                   sp["boards"][0, :n0], sp["boards"][1, :n1], sp["results"][0, :n0], fw]
+            assert int(g["total_moves"].item()) == int(g["moves"].sum().item())
+            assert n0 > 20 and n1 > 20 and int(sp["status"].sum()) == 0
+            if ref is None:
+                ref = [t.clone() for t in got]
+            else:
+                for k, (a, b) in enumerate(zip(ref, got)):
+                    assert torch.equal(a, b), (mode, k)
+        assert pkg._lib.take_error_flag() == 0
+    finally:
+        eng.set_latency_mode(2)
