@@ -669,19 +669,24 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
                                  : "memory");
             }
             named_bar(bar_id, GW * 32);
-            constexpr int PARTS = GW, PER = 64 / PARTS;  // threads per board, inputs per thread
-            const int t = j * 32 + lane, b = t / PARTS, part = t % PARTS;
+            // 8 threads per board, 8 inputs each, in BOTH variants (the 16-warp variant leaves half its threads out): the
+            // fp32 summation order, and with it every logit bit, is the same whichever kernel variant evaluates a board
+            constexpr int PARTS = 8, PER = 8;
+            const int t = j * 32 + lane, b = (t / PARTS) & 31, part = t % PARTS;
+            const bool fc_active = t < 32 * PARTS;
             const uint32_t ta = smem_u32(tail);
             float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (fc_active) {
 #pragma unroll
-            for (int i = 0; i < PER; i++) {
-                float x;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(hb + (uint32_t)(b * HEAD_STRIDE + part * PER + i) * 4));
+                for (int i = 0; i < PER; i++) {
+                    float x;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(hb + (uint32_t)(b * HEAD_STRIDE + part * PER + i) * 4));
 #pragma unroll
-                for (int o = 0; o < 4; o++) {
-                    float w;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(ta + (uint32_t)(TAIL_FCW + o * 64 + part * PER + i) * 4));
-                    z[o] = fmaf(x, w, z[o]);
+                    for (int o = 0; o < 4; o++) {
+                        float w;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(ta + (uint32_t)(TAIL_FCW + o * 64 + part * PER + i) * 4));
+                        z[o] = fmaf(x, w, z[o]);
+                    }
                 }
             }
 #pragma unroll
@@ -689,7 +694,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
 #pragma unroll
                 for (int sh = 1; sh < PARTS; sh <<= 1) z[o] += __shfl_xor_sync(0xffffffffu, z[o], sh);
             }
-            if (part == 0)
+            if (part == 0 && fc_active)
                 *reinterpret_cast<float4 *>(s_logits + b * 4) =
                     make_float4(z[0] + tail[TAIL_FCB + 0], z[1] + tail[TAIL_FCB + 1], z[2] + tail[TAIL_FCB + 2], z[3] + tail[TAIL_FCB + 3]);
             named_bar(bar_id, GW * 32);
