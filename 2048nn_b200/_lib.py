@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib2048nn_b200.so")
+# B2048_LIB selects another build of the same library (the -DB2048_DEBUG_ASSERTS variant of tools/debug_asserts_run.sh)
+LIB_PATH = os.environ.get("B2048_LIB") or os.path.join(_HERE, "lib2048nn_b200.so")
 
 u64, u32, i64, P = C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p
 

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib2048nn_b200.so")
+LIB = os.environ.get("B2048_LIB") or os.path.join(HERE, "lib2048nn_b200.so")  # B2048_LIB: build a variant elsewhere
 SOURCES = ["b2048_capi.cu", "b2048_train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

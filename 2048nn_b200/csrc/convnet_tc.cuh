@@ -211,6 +211,24 @@ __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
     return d;
 }
 
+// Debug build (-DB2048_DEBUG_ASSERTS, `B2048_EXP=B2048_DEBUG_ASSERTS python 2048nn_b200/build.py`): bounds checks on the shared /
+// tensor-memory addresses the epilogue and the MMA descriptors are built from, and a check of the mbarrier protocol's invariant
+// (the MMA warps start layer l of a set only when exactly l+1 act phases and l acc phases of the iteration have completed).
+// compute-sanitizer is closed on the B200 pool, so this is what stands in for racecheck: tools/debug_asserts_run.sh runs the
+// forward / playout / main-game workloads on the debug build; a violated assert traps the kernel (the launch fails loudly).
+#ifdef B2048_DEBUG_ASSERTS
+#define TC_ASSERT(cond)              \
+    do {                             \
+        if (!(cond)) __trap();       \
+    } while (0)
+#else
+#define TC_ASSERT(cond) do { } while (0)
+#endif
+// The act barrier completes N_LAYERS phases per forward and waiters use parity: a waiter more than one phase behind would see
+// an aliased parity.  The weight ring bounds how far the producer can run ahead of the MMA warps; with two slots it reaches the
+// next iteration's first act wait only after the MMA warps are in the current iteration's last layer.
+static_assert(RING == 2, "a deeper weight ring lets the producer's parity wait on the act barrier alias: re-derive the protocol first");
+
 #ifdef B2048_TRACE  // bring-up instrumentation: clock64 timeline of CTA 0 (iteration B2048_TRACE of each set)
 __device__ long long g_trace[512];
 #define TC_TRACE(iter, idx)                                                                  \
@@ -403,6 +421,9 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                                 continue;
                             }
                             any = true;
+#ifdef B2048_DEBUG_ASSERTS
+                            if (r == RUN_FWD) TC_ASSERT(*reinterpret_cast<volatile int *>(sm + SM_RUN + 32 * set + 16) == 1);
+#endif
                             if (r == RUN_IDLE) {
                                 skip[set] = true;
                                 phase[set]++;  // an idle iteration has this one act phase
@@ -412,6 +433,11 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                             }
                         }
                     }
+#ifdef B2048_DEBUG_ASSERTS
+                    // the workers cannot be more than this layer's input ahead: they wait for this layer's accumulators
+                    if (dyi == 0 && l > 0) TC_ASSERT(*reinterpret_cast<volatile int *>(sm + SM_RUN + 32 * set + 16) == l + 1);
+                    TC_ASSERT(slot < (uint32_t)RING && set * 256 + 256 <= TMEM_COLS);
+#endif
                     if (!have_chunk) {
                         mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
                         if (half == 0) TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
@@ -554,6 +580,13 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
     uint8_t *row0 = act + (size_t)act_row(x0, q, lane) * ROW_BYTES;
     uint8_t *row1 = act + (size_t)act_row(WIDE ? x0 : x0 + 1, q, lane) * ROW_BYTES;
     const int sw = lane & 7;  // SWIZZLE_128B phase of both rows (row index % 8 == lane % 8)
+#ifdef B2048_DEBUG_ASSERTS
+    volatile int *s_nact = reinterpret_cast<volatile int *>(sm + SM_RUN + 32 * set + 16);  // act phases published in this iteration
+    TC_ASSERT(x0 >= 0 && x0 + NX <= 4 && q >= 0 && q < 4);
+    TC_ASSERT(smem_u32(row0) + ROW_BYTES <= sm_base + SM_ACT + (set + 1) * ACT_BYTES && smem_u32(row0) >= sm_base + SM_ACT + set * ACT_BYTES);
+    TC_ASSERT((acc0 & 0xFFFFu) + NX * 64 <= (uint32_t)TMEM_COLS && (acc0 >> 16) < 128u);
+    TC_ASSERT((smem_u32(row0) & 127u) == 0 && ((smem_u32(row0) >> 7) & 7u) == (uint32_t)sw);
+#endif
     const int bar_id = 1 + set;
     typename Work::State ws;
     if (j == 0) Work::init(ws, wp, set);
@@ -608,6 +641,9 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
         }
         fence_proxy_async();
         __syncwarp();
+#ifdef B2048_DEBUG_ASSERTS
+        if (j == 0 && lane == 0) *s_nact = 1;  // this iteration's first act phase (the encoded boards)
+#endif
         if (lane == 0) mbar_arrive(bar_act);
         // long-latency preparation of the NEXT step (candidate moves) overlaps the first layer's MMAs
         if (j == 0) Work::prefetch(wp, ws, sm + SM_CAND + set * 2048, lane);
@@ -650,6 +686,9 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
             if (l < N_LAYERS - 1) {
                 fence_proxy_async();
                 __syncwarp();
+#ifdef B2048_DEBUG_ASSERTS
+                if (j == 0 && lane == 0) *s_nact = l + 2;  // owner warp's view; the phase completes when all warps arrived
+#endif
                 if (lane == 0) mbar_arrive(bar_act);
             }
             if (j == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 3);

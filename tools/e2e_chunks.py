@@ -1,0 +1,27 @@
+"""End-to-end fixed-order playouts through host buffers (engine.HostPlayout): pipeline depth sweep."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+pkg = importlib.import_module("2048nn_b200")
+eng = pkg.engine
+n = 1 << 24
+start = eng.init_boards(n, 777, 0)
+h_start = start.cpu().pin_memory()
+out = eng.playout_fixed(n, 1, 0, start=start)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for k in range(3):
+    eng.playout_fixed(n, 2 + k, 0, start=start, out=out)
+e1.record(); torch.cuda.synchronize()
+print(f"device-resident: {e0.elapsed_time(e1) / 3:.2f} ms per step", flush=True)
+for chunks in (2, 3, 4, 6, 8, 12, 16, 24, 32):
+    hp = eng.HostPlayout(n, chunks=chunks)
+    hp(h_start, 3000, 0)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(4):
+        hp(h_start, 4000 + k, 0)
+    e1.record(); torch.cuda.synchronize()
+    print(f"chunks={chunks:3d}: {e0.elapsed_time(e1) / 4:.2f} ms per step", flush=True)
+    del hp
