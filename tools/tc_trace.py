@@ -20,12 +20,11 @@ for l in range(7):
     for s in range(2):
         r = t[l * 2 + s]
         print(f"L{l} set{s}: " + "  ".join(f"{names[i]}={int(r[i]-t0) if r[i] else -1:7d}" for i in range(7 if s == 0 else 4)))
-tt = np.array(buf[:], dtype=np.int64)[256:320].reshape(2, 32)[:, :16]
-for s in range(2):
-    d = np.diff(tt[s])
-    print(f"set{s} L3 dy1 per-MMA issue intervals (slab order 0,3,1,2; N=128,128,192,192):", d.tolist(), "first-last", int(tt[s][-1] - tt[s][0]))
-e = np.array(buf[:], dtype=np.int64)[384:384 + 56].reshape(14, 4)
-for l in range(1, 6):
+print("per set-layer (cycles): issue window = mma:issued_dy2 - mma:act_ready (tensor floor 3840 for a 64-channel layer, 1920 for L0);"
+      " drain = wrk:acc_ready - mma:issued_dy2; epilogue = wrk:epi_done - wrk:acc_ready")
+for l in range(7):
     for s_ in range(2):
-        r = t[l * 2 + s_]; x = e[l * 2 + s_]
-        print(f"L{l} set{s_}: acc_ready->chunks_done {int(x[0]-r[2])}  tc_fence_before {int(x[1]-x[0])}  fence.proxy.async {int(x[2]-x[1])}  arrive {int(r[3]-x[2])}")
+        r = t[l * 2 + s_]
+        print(f"L{l} set{s_}: issue window {int(r[1]-r[0]):6d}  drain {int(r[2]-r[1]):6d}  epilogue {int(r[3]-r[2]):6d}")
+r0, r1 = t[0], t[13]
+print("forward of both sets, first act_ready -> last epilogue done:", int(max(t[12][3], t[13][3]) - min(t[0][0], t[1][0])), "cycles")
