@@ -303,9 +303,8 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
 }
 
 // ---- producer warp: weights ---------------------------------------------------------------------
-// One "iteration" = one forward of every active set.  Each 24 KB chunk (layer, dy) is loaded ONCE per
-// iteration and consumed by both sets back to back, so the ring's two slots cover twice the MMA time.
-// Mirrors the MMA warp's control flow (same run flags, same chunk order).
+// One "iteration" = one forward of every active set.  Mirrors the MMA warps' control flow (same run flags, same chunk
+// order): set-major, i.e. per layer the three chunks for set A, then the same three again for set B (mma_loop says why).
 __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob, int nsets, int n_chunks) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
@@ -317,6 +316,7 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob, 
     uint32_t prod = 0;
     for (;;) {
         bool any = false, load = false;
+        int nrun = 0;  // sets that run a forward in this iteration
         for (int set = 0; set < NSETS; set++) {
             if (!active[set]) continue;
             // the set's workers publish their decision before their first act arrival of the iteration
@@ -329,35 +329,38 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob, 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars.idle0 + 8 * set);
             } else {
-                any = true, load = true, ph[set] += N_LAYERS;
+                any = true, load = true, nrun++, ph[set] += N_LAYERS;
             }
         }
         if (!any) break;
         if (!load) continue;  // every running set idles: the MMA warps consume no chunk in this iteration either
         if (lane == 0) {
-            for (int c = 0; c < n_chunks; c++) {
-                const uint32_t slot = prod % RING, use = prod / RING;
-                if (use > 0) mbar_wait(bars.empty0 + 8 * slot, (use - 1) & 1);
-#ifdef B2048_EXP_SMALL_W  // timing experiment only: load 1/6 of every chunk (wrong results)
-                mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES / 6);
-                bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES / 6,
-                         bars.full0 + 8 * slot);
+#ifdef B2048_DY_INTERLEAVED
+            const int reps = 1;  // each chunk serves both sets back to back
 #else
-                mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES);
-                bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
-                         bars.full0 + 8 * slot);
+            // set-major order (see mma_loop): with two running sets every layer's three chunks stream twice
+            const int reps = (n_chunks == N_CHUNKS && nrun == 2) ? 2 : 1;
 #endif
-                prod++;
-            }
+            const int per_layer = reps == 2 ? 3 : n_chunks;  // reps == 1: one pass over the whole stream
+            for (int c0 = 0; c0 < n_chunks; c0 += per_layer)
+                for (int rep = 0; rep < reps; rep++)
+                    for (int c = c0; c < c0 + per_layer; c++) {
+                        const uint32_t slot = prod % RING, use = prod / RING;
+                        if (use > 0) mbar_wait(bars.empty0 + 8 * slot, (use - 1) & 1);
+                        mbar_expect_tx(bars.full0 + 8 * slot, CHUNK_BYTES);
+                        bulk_g2s(sm_base + SM_RING + slot * CHUNK_BYTES, blob + (size_t)c * CHUNK_BYTES, CHUNK_BYTES,
+                                 bars.full0 + 8 * slot);
+                        prod++;
+                    }
         }
         prod = __shfl_sync(0xffffffffu, prod, 0);
     }
 }
 
 // ---- MMA warps -----------------------------------------------------------------------------------------
-// Unit order per layer: chunk dy=-1 [set A, set B], dy=0 [A, B], dy=+1 [A, B].  A set's accumulators are
-// committed after its dy=+1 part, so its epilogue overlaps the other set's last third and the next layer's
-// first MMAs of the other set (ping-pong).
+// Unit order per layer: set A's chunks dy=-1, 0, +1, then set B's (set-major; the round-1 order dy=-1 [A, B], dy=0 [A, B],
+// dy=+1 [A, B] is kept under -DB2048_DY_INTERLEAVED for A/B runs).  A set's accumulators are committed after its dy=+1
+// part, so its epilogue overlaps the other set's whole layer (ping-pong).
 //
 // Measured on B200 (tools/tc_trace.py): a single thread needs ~100-125 cycles per tcgen05.mma (descriptor
 // arithmetic, R2UR moves, election), more than the tensor pipe needs for N <= 192 (64-96 cycles).  The
@@ -404,6 +407,72 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
         trace_iter++;
         for (int l = 0; l < N_LAYERS; l++) {
             const int nk = (l == 0) ? 2 : 4;  // K steps of 16 channels (L0: one-hot x [hi | lo])
+#ifndef B2048_DY_INTERLEAVED
+            // Set-major order: all three dy chunks of set A, then all three of set B.  A set's epilogue chain (drain of the
+            // last MMAs ~300 cycles, TMEM -> registers -> fp16 -> shared ~2,000-3,400, act barrier ~500: ~2,700-4,000 in
+            // all) then hides behind the other set's WHOLE layer (3,840 tensor cycles).  The dy-interleaved order
+            // [A,B,A,B,A,B], which lets a chunk serve both sets, leaves it one third of that: measured 10,400 cycles per
+            // layer pair against the 7,680-cycle tensor floor (profiles/r02_tc_trace_dy_interleaved.txt).  The price is that
+            // a layer's chunks stream from L2 twice when both sets run (the ring holds two chunks, not a layer).
+            for (int set = 0; set < NSETS; set++) {
+                if (!active[set]) continue;
+                if (l == 0) skip[set] = false;
+                if (skip[set]) continue;  // the set idles in this iteration
+                for (int dyi = 0; dyi < 3; dyi++) {
+                    if (dyi == 0) {
+                        mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
+                        if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
+                        if (l == 0) {
+                            const int r = s_run[8 * set];
+                            if (r == RUN_STOP) {
+                                active[set] = false;
+                                break;
+                            }
+                            any = true;
+#ifdef B2048_DEBUG_ASSERTS
+                            if (r == RUN_FWD) TC_ASSERT(*reinterpret_cast<volatile int *>(sm + SM_RUN + 32 * set + 16) == 1);
+#endif
+                            if (r == RUN_IDLE) {
+                                skip[set] = true;
+                                phase[set]++;  // an idle iteration has this one act phase
+                                __syncwarp();
+                                if ((threadIdx.x & 31) == 0) mbar_arrive(bars.idle0 + 8 * set);
+                                break;
+                            }
+                        }
+#ifdef B2048_DEBUG_ASSERTS
+                        if (l > 0) TC_ASSERT(*reinterpret_cast<volatile int *>(sm + SM_RUN + 32 * set + 16) == l + 1);
+#endif
+                    }
+                    uint32_t slot = cons % RING;
+                    mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                    if (half == 0 && set == 0) TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
+                    tc_fence_after();
+                    // whole warp, uniform operands, one elected lane issues; tmem_base is 0 (all 512 columns owned)
+                    issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                               (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16);
+                    if (PRECISE && layer_is_split(l)) {
+                        // precise mode (one set): + x_lo * w_hi on the same chunk, then the layer's lo chunk: + x_hi * w_lo
+                        issue_half((sm_base + SM_ACT + ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                        umma_commit_elect(bars.empty0 + 8 * slot);
+                        cons++;
+                        slot = cons % RING;
+                        mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                        tc_fence_after();
+                        issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                    }
+                    umma_commit_elect(bars.empty0 + 8 * slot);  // this half's "slot reusable"
+                    cons++;
+                    if (dyi == 2) {
+                        umma_commit_elect(bars.acc0 + 8 * set);  // this half of the set's accumulators
+                        if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
+                        phase[set]++;
+                    }
+                }
+            }
+#else
             for (int dyi = 0; dyi < 3; dyi++) {
                 const uint32_t slot = cons % RING;
                 bool have_chunk = false;
@@ -471,6 +540,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                     cons++;
                 }
             }
+#endif
             if (l == 0 && !any) return;
         }
     }
