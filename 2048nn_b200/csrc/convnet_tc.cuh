@@ -57,7 +57,10 @@ constexpr int PRODUCER_WARP = WORKER_WARPS;       // warp 16
 constexpr int MMA_WARP = WORKER_WARPS + 1;        // warps 17, 18: MMA issuers of accumulator halves 0 / 1 (19 idle)
 constexpr int NUM_WARPS = WORKER_WARPS + 4;
 constexpr int NUM_THREADS = NUM_WARPS * 32;       // 640
-constexpr int WORKER_REGS = 104, CONTROL_REGS = 56;  // setmaxnreg pool = launch allocation 640 x 96 = 61,440 >= 16*32*104 + 4*32*56
+#ifndef B2048_CONTROL_REGS
+#define B2048_CONTROL_REGS 56
+#endif
+constexpr int WORKER_REGS = 104, CONTROL_REGS = B2048_CONTROL_REGS;  // setmaxnreg pool = launch allocation 640 x 96 = 61,440 >= 16*32*104 + 4*32*56
 constexpr int TMEM_COLS = 512;
 
 // Precise mode (B2048_PREC_FP16X2_TC): the three most error-sensitive layers L1..L3 take BOTH operands as fp16 hi + lo
@@ -266,7 +269,7 @@ constexpr int N_CONTROL_WARPS = 3;
 
 // ---- CTA setup / teardown ----------------------------------------------------------------------
 __device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *blob, uint32_t &tmem_base, int group_warps,
-                                             int blob_w_bytes) {
+                                             int blob_w_bytes, int issuers_per_set) {
     uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sm_base = smem_u32(sm);
     const int tid = threadIdx.x;
@@ -278,10 +281,10 @@ __device__ __forceinline__ uint8_t *tc_setup(uint8_t *smem_raw, const uint8_t *b
         Bars b(sm_base);
         for (int i = 0; i < RING; i++) {
             mbar_init(b.full0 + 8 * i, 1);
-            mbar_init(b.empty0 + 8 * i, 2);  // one arrival per MMA-issuing warp
+            mbar_init(b.empty0 + 8 * i, issuers_per_set);  // one arrival per MMA warp that consumes the chunk
         }
         for (int i = 0; i < NSETS; i++) {
-            mbar_init(b.acc0 + 8 * i, 2);            // tcgen05.commit of the two MMA-issuing warps
+            mbar_init(b.acc0 + 8 * i, issuers_per_set);  // tcgen05.commit of the set's MMA-issuing warp(s)
             mbar_init(b.act0 + 8 * i, group_warps);  // one arrival per worker warp of the set
             mbar_init(b.idle0 + 8 * i, N_CONTROL_WARPS);
         }
@@ -362,11 +365,12 @@ __device__ __forceinline__ void producer_loop(uint8_t *sm, const uint8_t *blob, 
 // dy=+1 [A, B] is kept under -DB2048_DY_INTERLEAVED for A/B runs).  A set's accumulators are committed after its dy=+1
 // part, so its epilogue overlaps the other set's whole layer (ping-pong).
 //
-// Measured on B200 (tools/tc_trace.py): a single thread needs ~100-125 cycles per tcgen05.mma (descriptor
-// arithmetic, R2UR moves, election), more than the tensor pipe needs for N <= 192 (64-96 cycles).  The
-// issue work of every unit is therefore split over TWO warps that own disjoint halves of the accumulator:
+// One tile-set per CTA (latency / precise variants) -- two-halves scheme.  Measured on B200 (tools/tc_trace.py): a single
+// thread needs ~100-125 cycles per tcgen05.mma (descriptor arithmetic, R2UR moves, election), more than the tensor pipe
+// needs for N <= 192 (64-96 cycles).  The issue work of every unit is therefore split over TWO warps that own disjoint
+// halves of the accumulator (two tile-sets per CTA use issue_set below instead: one warp per set):
 //   half 0 -> output column blocks {0,1}:  slab 0 (N=128), slab 1 (N=128), slab 2 (N=64: block 1 only)
-//   half 1 -> output column blocks {2,3}:  slab 3 (N=128), slab 2 (N=128), slab 1 (N=64: block 2 only)
+//   half 1 -> output column blocks {2,3}:  slab 3 (N=128), slab 1 (N=64: block 2 only), slab 2 (N=128)
 // Same tensor work as one N=128/192/192/128 sweep, each half's first MMA (dy=-1, k=0) is its own first
 // writer (overwrite), and no ordering between the two issuers is needed.
 __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi,
@@ -374,10 +378,15 @@ __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         // (slab, first B row, N, first D column) of this half's i-th MMA group; chunk rows are
-        // [dx=+1 -> x=s-1 | dx=0 -> x=s | dx=-1 -> x=s+1] x 64
-        const int s = half == 0 ? i : 3 - i;
-        const int brow = half == 0 ? (i == 0 ? 64 : 0) : (i == 0 ? 0 : (i == 1 ? 64 : 128));
-        const int N = (i == 2) ? 64 : 128;
+        // [dx=+1 -> x=s-1 | dx=0 -> x=s | dx=-1 -> x=s+1] x 64.
+        //   half 0: slab 0 -> blocks {0,1}, slab 1 -> {0,1}, slab 2 -> {1}
+        //   half 1: slab 3 -> blocks {2,3}, slab 1 -> {2},   slab 2 -> {2,3}
+        // Slab order per output block = 0,1,2 (block 1) and 3,1,2 (block 2): the order in which issue_set (one warp per set,
+        // slabs 0,3,1,2 with N = 192 groups) accumulates them, so both schemes add the same terms in the same order and a
+        // board's logits are bit-identical whichever kernel variant evaluates it.
+        const int s = half == 0 ? i : (i == 0 ? 3 : i);
+        const int brow = half == 0 ? (i == 0 ? 64 : 0) : (i == 0 ? 0 : (i == 1 ? 128 : 64));
+        const int N = half == 0 ? (i == 2 ? 64 : 128) : (i == 1 ? 64 : 128);
         const int dcol = half == 0 ? (i == 2 ? 64 : 0) : 128;
         const uint32_t idesc = make_idesc(128, N, bf16);
         // 16-byte units: a slab-row group is 32 rows x 128 B = 256 units; a K step is 2 units
@@ -391,7 +400,39 @@ __device__ __forceinline__ void issue_half(uint32_t in_lo, uint32_t w_lo, uint32
     }
 }
 
-template <bool PRECISE>
+// ---- MMA warps, two tile-sets: ONE issuing warp per set -------------------------------------------------------------
+// With two sets per CTA, warp 17 issues every MMA of set A and warp 18 every MMA of set B.  Per (dy, k) a set then needs four
+// tcgen05.mma, one per input slab with N = 128 / 192 / 192 / 128 (an A operand read once feeds up to three output columns):
+// 48 per layer instead of the 72 of the two-halves scheme, and a warp has a whole layer PAIR (7,680 tensor cycles) to issue
+// them, so the tensor pipe -- not instruction issue -- sets the pace (two-halves scheme, measured: 4,400-cycle issue window
+// per set and layer against the 3,840-cycle floor).  All accumulations of a set come from one thread in program order, so
+// the fp32 summation order -- every logit bit -- is fixed.  (Sharing the N = 192 groups between two warps of one set was
+// measured faster still but the two warps then accumulate into the same TMEM columns in a timing-dependent order: the
+// forward was no longer bit-reproducible.  Rejected.)
+// Chunk stream (producer_loop): per layer the three chunks of set A, then the three of set B, for the sets that run.
+// Both MMA warps still walk through every act phase of both sets and every fill of the weight ring (mma_loop, PER_SET): an
+// mbarrier wait identifies a phase by parity only, so a waiter must never be more than one phase away from the barrier.
+__device__ __forceinline__ void issue_set(uint32_t in_lo, uint32_t w_lo, uint32_t acc_base, uint64_t desc_hi, int dyi, int nk,
+                                          bool bf16) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // slab order 0, 3, 1, 2: the first writers of blocks {0,1} (slab 0) and {2,3} (slab 3) come first
+        const int s = (i == 0) ? 0 : (i == 1) ? 3 : (i == 2) ? 1 : 2;
+        const int brow = (s == 0) ? 64 : 0;             // slab 0 has no x = -1 output
+        const int N = (s == 0 || s == 3) ? 128 : 192;   // slab 3 has no x = 4 output
+        const int dcol = (s == 0) ? 0 : (s - 1) * 64;
+        const uint32_t idesc = make_idesc(128, N, bf16);
+        const uint32_t a_lo = in_lo + (uint32_t)((5 * s + dyi) * 256);
+        const uint32_t b_lo = w_lo + (uint32_t)(brow * 8);
+        const uint32_t d_addr = acc_base + (uint32_t)dcol;
+        for (int k = 0; k < nk; k++) {
+            const uint32_t acc = (dyi == 0 && k == 0 && i < 2) ? 0u : 1u;
+            umma_f16_elect(d_addr, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, acc);
+        }
+    }
+}
+
+template <bool PRECISE, bool PER_SET>
 __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int nsets) {
     const uint32_t sm_base = smem_u32(sm);
     const Bars bars(sm_base);
@@ -421,7 +462,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                 for (int dyi = 0; dyi < 3; dyi++) {
                     if (dyi == 0) {
                         mbar_wait(bars.act0 + 8 * set, phase[set] & 1);  // this layer's input image is complete
-                        if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
+                        if (PER_SET ? set == half : half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 0);
                         if (l == 0) {
                             const int r = s_run[8 * set];
                             if (r == RUN_STOP) {
@@ -445,6 +486,26 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
 #endif
                     }
                     uint32_t slot = cons % RING;
+                    if (PER_SET) {
+                        // One issuing warp per set (issue_set).  BOTH MMA warps still walk through every act phase and every
+                        // weight-ring fill in order: an mbarrier wait names a phase only by its parity, so a warp that skipped
+                        // the fills meant for the other set would take an older fill of the same slot for its own (found on
+                        // the GPU: the kernel faulted until the non-consuming warp waited too).
+                        mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                        if (set == half) {
+                            tc_fence_after();
+                            issue_set((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
+                                      (uint32_t)(set * 256), desc_hi, dyi, nk, bf16);
+                            umma_commit_elect(bars.empty0 + 8 * slot);  // the only consumer of this chunk
+                        }
+                        cons++;
+                        if (dyi == 2) {
+                            if (set == half) umma_commit_elect(bars.acc0 + 8 * set);
+                            if (set == half) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
+                            phase[set]++;
+                        }
+                        continue;
+                    }
                     mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
                     if (half == 0 && set == 0) TC_TRACE(trace_iter, (l * 2 + 0) * 8 + 4 + dyi);
                     tc_fence_after();
@@ -821,8 +882,13 @@ tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float 
     extern __shared__ uint8_t smem_raw[];
     blob += Work::blob_offset(wp);
     uint32_t tmem_base;
+#ifdef B2048_DY_INTERLEAVED
+    constexpr bool PER_SET = false;
+#else
+    constexpr bool PER_SET = !WIDE;  // two tile-sets: one issuing warp per set; one tile-set: two warps on accumulator halves
+#endif
     uint8_t *sm = tc_setup(smem_raw, blob, tmem_base, WIDE ? WORKER_WARPS : GROUP_WARPS,
-                           PRECISE ? BLOB_W_BYTES_PRECISE : BLOB_W_BYTES);
+                           PRECISE ? BLOB_W_BYTES_PRECISE : BLOB_W_BYTES, PER_SET ? 1 : 2);
     const int warp = threadIdx.x >> 5;
     constexpr int nsets = WIDE ? 1 : NSETS;
     if (warp < WORKER_WARPS) {
@@ -832,7 +898,9 @@ tc_persistent_kernel(const typename Work::Params wp, const uint8_t *blob, float 
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CONTROL_REGS));
         if (warp == PRODUCER_WARP) producer_loop(sm, blob, nsets, PRECISE ? N_CHUNKS_PRECISE : N_CHUNKS);
-        else if (warp == MMA_WARP || warp == MMA_WARP + 1) mma_loop<PRECISE>(sm, warp - MMA_WARP, BF16, nsets);
+        else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+            mma_loop<PRECISE, PER_SET>(sm, warp - MMA_WARP, BF16, nsets);
+        }
     }
     tc_teardown(tmem_base);
 }
