@@ -34,6 +34,7 @@ static Tables tables_of(const b2048_ctx *c) {
     t.score = c->score;
     t.legal = c->legal;
     t.rowstat = c->rowstat;
+    t.pair = c->pair;
     return t;
 }
 
@@ -61,7 +62,8 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->moved_rev, 65536));
     CK(cudaMalloc(&c->legal, 65536));
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
-    c->k2_variant = 1;
+    CK(cudaMalloc(&c->pair, K3_ROWS * sizeof(uint32_t)));
+    c->k2_variant = 2;
     c->tc_wide = 2;
     // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
     // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
@@ -73,7 +75,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->err_flag, 2 * sizeof(int)));
     CK(cudaMemset(c->err_flag, 0, 2 * sizeof(int)));
     build_tables_kernel<<<LC(c, 65536 / 256), 256>>>(c->fin_fwd, c->fin_rev, c->score, c->moved_fwd, c->moved_rev,
-                                              c->legal, c->rowstat, c->err_flag + 1);
+                                              c->legal, c->rowstat, c->pair, c->err_flag + 1);
     CK(cudaGetLastError());
     int mism = 0;
     CK(cudaMemcpy(&mism, c->err_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
@@ -82,6 +84,8 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(playout_fixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CK(cudaFuncSetAttribute(playout_fixed_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V2_SMEM_BYTES));
     CK(cudaFuncSetAttribute(playout_fixed_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V2_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(playout_fixed_kernel3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V3_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(playout_fixed_kernel3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2V3_SMEM_BYTES));
     CK(cudaFuncSetAttribute(convnet_fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             CN_FP32_SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -127,6 +131,7 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
     cudaFree(c->moved_rev);
     cudaFree(c->legal);
     cudaFree(c->rowstat);
+    cudaFree(c->pair);
     cudaFree(c->counters);
     cudaFree(c->err_flag);
     delete c;
@@ -143,7 +148,7 @@ extern "C" int b2048_set_latency_mode(b2048_ctx *c, int mode) {
 }
 
 extern "C" int b2048_set_playout_variant(b2048_ctx *c, int variant) {
-    if (variant != 0 && variant != 1) return fail_msg("b2048_set_playout_variant: variant must be 0 or 1");
+    if (variant < 0 || variant > 2) return fail_msg("b2048_set_playout_variant: variant must be 0, 1 or 2");
     c->k2_variant.store(variant);
     return 0;
 }
@@ -291,7 +296,13 @@ static int launch_playout(b2048_ctx *c, PlayParams &p, cudaStream_t st) {
         grid = (int)((p.n + block - 1) / block);
     }
     bool ludr = p.order[0] == 0 && p.order[1] == 1 && p.order[2] == 3 && p.order[3] == 2;
-    if (c->k2_variant.load() == 1) {
+    const int variant = c->k2_variant.load();
+    if (variant == 2) {
+        if (ludr)
+            playout_fixed_kernel3<true><<<LC(c, grid), block, K2V3_SMEM_BYTES, st>>>(p);
+        else
+            playout_fixed_kernel3<false><<<LC(c, grid), block, K2V3_SMEM_BYTES, st>>>(p);
+    } else if (variant == 1) {
         if (ludr)
             playout_fixed_kernel2<true><<<LC(c, grid), block, K2V2_SMEM_BYTES, st>>>(p);
         else

@@ -25,7 +25,13 @@ struct Tables {
     const uint32_t *score;
     const uint8_t *legal;  // u8[65536]: bit 0 = row moves toward nibble 0, bit 1 = toward nibble 3
     const uint2 *rowstat;  // [65536] per row: .x = sum (t-1)*2^t ("potential"), .y = sum 2^t (tile sum)
+    const uint32_t *pair;  // u32[K3_ROWS]: fin_fwd | fin_rev << 16 for the rows whose nibble 3 is below 14
 };
+// K2 variant 2 keeps `pair` in shared memory: 0xE000 rows x 4 B = 224 KB of the 227 KB a CTA may have.  A row index
+// >= K3_ROWS needs a tile 2^14 or 2^15 in board column 3 / row 3, i.e. a tile sum >= 16384; games hand over to the
+// exact global-table path before that can happen (the same hand-over that guards the 32768+32768 annihilation).
+#define K3_ROWS 0xE000u
+#define K3_TILESUM_MAX 16384u
 
 // board.py:104-132 move_row restated for one thread (used only to BUILD the tables on device).
 __device__ __forceinline__ void row_slide(u32 row, bool rev, u32 &fin, u32 &score) {
@@ -64,8 +70,17 @@ __device__ __forceinline__ u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) |
 // board.py:46-54 transpose.  Stage 1 swaps nibbles inside each 2x2 block and never leaves a
 // 32-bit half; stage 2 swaps the off-diagonal 2x2 blocks, which is a byte permutation of the
 // two halves (PRMT): bytes [B0..B7] -> [B0,B4,B2,B6 | B1,B5,B3,B7].
+// (written as a delta swap in PTX lop3 so that it stays 4 instructions -- SHF, LOP3, IMAD.SHL, LOP3 -- one of them off the
+// ALU pipe; the C expression is re-associated into 5)
+template <int LUT>
+__device__ __forceinline__ u32 lop3(u32 a, u32 b, u32 c) {
+    u32 r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
 __device__ __forceinline__ u32 tr_stage1(u32 h) {
-    return (h & 0xF0F00F0Fu) | ((h & 0x0000F0F0u) << 12) | ((h >> 12) & 0x0000F0F0u);
+    const u32 t = lop3<0x28>(h, h >> 12, 0x0000F0F0u);  // (h ^ (h >> 12)) & mask
+    return lop3<0x96>(h, t, t << 12);                   // h ^ t ^ (t << 12)
 }
 __device__ __forceinline__ u64 transpose(u64 x) {
     u32 a = tr_stage1(lo32(x)), b = tr_stage1(hi32(x));
@@ -117,20 +132,35 @@ __device__ __forceinline__ u32 rng_word(u64 key, u32 w) {
 // Precondition: 1 <= #empty <= 15 (callers route 0/16 to the error path).
 // Selecting the pos-th empty cell: prefix counts of the empty mask by one multiply
 // (mask * 0x11111111 puts #empties in nibbles 0..k into nibble k), then a SWAR compare.
+// Written for the ALU pipe, which bounds the playout kernels: empty mask in 3 instructions (the add may issue on the FMA
+// pipe), the 2-or-4 choice folded into the final shift, the tile ORed into its half by two predicated instructions.
 // ---------------------------------------------------------------------------------------
+// bit 4k+3 set when nibble k is empty: (h & 7..7) + 7..7 carries into bit 3 of every nonzero nibble (3 instructions,
+// the add can go to the FMA pipe)
+__device__ __forceinline__ u32 empty_mask32_hi(u32 h) { return ~(((h & 0x77777777u) + 0x77777777u) | h) & 0x88888888u; }
 __device__ __forceinline__ u64 spawn_tile(u64 board, u64 draw, u32 &is_four) {
-    u32 zl = empty_mask32(lo32(board)), zh = empty_mask32(hi32(board));
-    u32 cl = __popc(zl);
-    u32 n = cl + __popc(zh);
+    u32 lo = lo32(board), hi = hi32(board);
+    const u32 zl = empty_mask32_hi(lo), zh = empty_mask32_hi(hi);
+    const u32 cl = __popc(zl);
+    const u32 n = cl + __popc(zh);
     u32 pos = __umulhi(hi32(draw), n);
-    is_four = (__umulhi(lo32(draw), 10u) == 0u) ? 1u : 0u;
-    bool in_hi = pos >= cl;
-    u32 z = in_hi ? zh : zl;
+    const bool four = __umulhi(lo32(draw), 10u) == 0u;
+    is_four = four ? 1u : 0u;
+    const bool in_hi = pos >= cl;
+    const u32 z = (in_hi ? zh : zl) >> 3;
     pos -= in_hi ? cl : 0u;
-    u32 t = (z + 7u - pos) * 0x11111111u;  // nibble k >= 8  <=>  #empties in nibbles 0..k > pos
-    u32 m = t & 0x88888888u;
-    u32 tile = ((m & (0u - m)) >> 3) << is_four;
-    return in_hi ? (board | ((u64)tile << 32)) : (board | (u64)tile);
+    const u32 t = (z + 7u - pos) * 0x11111111u;  // nibble k >= 8  <=>  #empties in nibbles 0..k > pos
+    const u32 m = t & 0x88888888u;
+    const u32 tile = (m & (0u - m)) >> (four ? 2u : 3u);
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p or.b32 %0, %0, %3;\n\t"
+        "@!p or.b32 %1, %1, %3;\n\t"
+        "}"
+        : "+r"(hi), "+r"(lo)
+        : "r"((u32)in_hi), "r"(tile));  // two predicated ORs instead of two selects and two ORs
+    return pack64(lo, hi);
 }
 
 // generate_init_tiles (board.py:68-82) on the game's word stream (words 0..15 reserved).

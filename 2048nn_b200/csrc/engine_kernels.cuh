@@ -9,7 +9,7 @@ namespace b2048 {
 // Table build on the device (replaces board.py:134-148).  One thread per row.
 // ---------------------------------------------------------------------------------------
 __global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32_t *score, uint8_t *moved_fwd,
-                                    uint8_t *moved_rev, uint8_t *legal, uint2 *rowstat, int *mismatch) {
+                                    uint8_t *moved_rev, uint8_t *legal, uint2 *rowstat, uint32_t *pair, int *mismatch) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= 65536) return;
     u32 ff, sf, fr, sr;
@@ -22,6 +22,7 @@ __global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32
     moved_rev[r] = fr != r;
     legal[r] = (uint8_t)((ff != r) | ((fr != r) << 1));
     rowstat[r] = make_uint2(potential((u64)r), tile_sum((u64)r));
+    if (r < K3_ROWS) pair[r] = ff | (fr << 16);  // both slides of a row in one word (K2 variant 2)
     // invariants the playout kernel relies on: equal scores, mirrored finals
     u32 mf, ms;
     row_slide(mirror32(r) & 0xFFFFu, false, mf, ms);
@@ -620,6 +621,222 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
             long r = slot / p.number;
             if (p.out_logsum) {
                 double t = log10((double)score + (double)rs + 1.0);
+                long long q = __double2ll_rn(ldexp(t, 40));
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
+            }
+            if (p.out_count) atomicAdd(p.out_count + r, 1);
+            if (p.out_minmov) atomicMin(p.out_minmov + r, (int)count);
+        }
+        have = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 variant 2 (default): the pair table.
+//
+// ncu on variant 1 (profiles/r02_k2_playout_fixed_ncu.txt): ALU pipe 88 % busy, shared-memory wavefronts 86 % of peak,
+// 174 executed thread-instructions per move -- the kernel is bound by the NUMBER of ALU-pipe instructions and of
+// shared-memory lookups per move.  This variant removes both kinds of work instead of rescheduling it:
+//  * one u32 table entry per row holds BOTH slides (toward nibble 0 in the low half, toward nibble 3 in the high half),
+//    so 8 lookups (4 rows of the board, 4 rows of its transpose) give all four candidate boards: no legality table (legal
+//    <=> candidate != board), no mirror(), no second round of lookups for the chosen direction -- 8 LDS.32 per move
+//    instead of 8 LDS.U8 + 4 LDS.U16;
+//  * the table covers rows < K3_ROWS (224 KB of shared memory, filled by cp.async.bulk); a larger row index needs a tile
+//    sum >= 16384, and a game hands over to the exact global-table path before that is possible (the hand-over that
+//    already guards the 32768+32768 annihilation, so it costs nothing per move);
+//  * K3_UNROLL moves per pass of the outer loop (the refill vote is paid once per pass), the spawn's draw counter folded
+//    into the key (two IMADs per draw), transposes as 4-instruction delta swaps, a 3-instruction empty mask.
+// Bit-exact with variants 0 and 1 (tests/test_engine_gpu.py).
+// ---------------------------------------------------------------------------------------
+#define K2V3_SMEM_BYTES (K3_ROWS * 4)
+#ifndef K3_UNROLL
+#define K3_UNROLL 4
+#endif
+
+__device__ __forceinline__ void k3_bulk_load(void *smem_dst, const void *gsrc, u32 bytes, unsigned long long *bar) {
+    const u32 b = (u32)__cvta_generic_to_shared(bar), d = (u32)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        for (u32 off = 0; off < bytes; off += 32768u) {
+            const u32 n = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d + off),
+                         "l"((const char *)gsrc + off), "r"(n), "r"(b)
+                         : "memory");
+        }
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "K3_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0, 0x989680;\n\t"
+        "@P1 bra K3_DONE;\n\t"
+        "bra K3_WAIT;\n\t"
+        "K3_DONE:\n\t"
+        "}" ::"r"(b)
+        : "memory");
+}
+
+// byte offsets of the two rows of a 32-bit half in the pair table
+__device__ __forceinline__ u32 k3_off_lo(u32 h) { return (h << 2) & 0x3FFFCu; }
+__device__ __forceinline__ u32 k3_off_hi(u32 h) { return (h >> 14) & 0x3FFFCu; }  // (IMAD.HI instead of SHF measured slower)
+__device__ __forceinline__ u32 k3_ld(u32 smem_base, u32 off) {
+    u32 v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_base + off));  // read-only after k3_bulk_load
+    return v;
+}
+
+// One move of one game on the pair table.  Returns false when the game cannot go on here: the board is dead, or the
+// move budget of the table path is used up (`count >= limit`: tile sum may reach K3_TILESUM_MAX).
+template <bool LUDR>
+__device__ __forceinline__ bool k3_step(u32 sbase, u64 &b, u64 keyc, u32 &count, u32 &n4, u32 limit, u32 o0, u32 o1, u32 o2,
+                                        u32 o3) {
+    if (count >= limit) return false;
+    const u64 bt = transpose(b);
+    const u32 lo = lo32(b), hi = hi32(b), tlo = lo32(bt), thi = hi32(bt);
+    const u32 e0 = k3_ld(sbase, k3_off_lo(lo)), e1 = k3_ld(sbase, k3_off_hi(lo));
+    const u32 e2 = k3_ld(sbase, k3_off_lo(hi)), e3 = k3_ld(sbase, k3_off_hi(hi));
+    const u32 c0 = k3_ld(sbase, k3_off_lo(tlo)), c1 = k3_ld(sbase, k3_off_hi(tlo));
+    const u32 c2 = k3_ld(sbase, k3_off_lo(thi)), c3 = k3_ld(sbase, k3_off_hi(thi));
+    const u32 Ll = __byte_perm(e0, e1, 0x5410), Lh = __byte_perm(e2, e3, 0x5410);  // Left  (rows of b, toward nibble 0)
+    const u32 Rl = __byte_perm(e0, e1, 0x7632), Rh = __byte_perm(e2, e3, 0x7632);  // Right
+    const u32 Ul = __byte_perm(c0, c1, 0x5410), Uh = __byte_perm(c2, c3, 0x5410);  // Up    (rows of bt)
+    const u32 Dl = __byte_perm(c0, c1, 0x7632), Dh = __byte_perm(c2, c3, 0x7632);  // Down
+    const bool lL = (Ll != lo) | (Lh != hi), lR = (Rl != lo) | (Rh != hi);
+    const bool lU = (Ul != tlo) | (Uh != thi), lD = (Dl != tlo) | (Dh != thi);
+    if (!(lL | lR | lU | lD)) return false;
+    u32 vl, vh, hl, hh;
+    bool vert;
+    if (LUDR) {  // Left, else Up, else Down, else Right
+        vl = lU ? Ul : Dl, vh = lU ? Uh : Dh;
+        hl = lL ? Ll : Rl, hh = lL ? Lh : Rh;
+        vert = !lL & (lU | lD);
+    } else {
+        const u32 mask = (u32)lL | ((u32)lU << 1) | ((u32)lR << 2) | ((u32)lD << 3);
+        const u32 d = ((mask >> o0) & 1u) ? o0 : ((mask >> o1) & 1u) ? o1 : ((mask >> o2) & 1u) ? o2 : o3;
+        const bool fwd = (d & 2u) == 0;
+        vl = fwd ? Ul : Dl, vh = fwd ? Uh : Dh;
+        hl = fwd ? Ll : Rl, hh = fwd ? Lh : Rh;
+        vert = (d & 1u) != 0;
+    }
+    const u64 tv = transpose(pack64(vl, vh));
+    const u64 y = vert ? tv : pack64(hl, hh);
+    u32 four;
+    b = spawn_tile(y, mix64(keyc + (u64)count * B2048_GOLDEN), four);  // = rng_draw(key, INIT_DRAWS + spawn0 + count)
+    n4 += four;
+    count++;
+    return true;
+}
+
+template <bool LUDR>
+__global__ void __launch_bounds__(1024, 1) playout_fixed_kernel3(const PlayParams p) {
+    extern __shared__ __align__(128) u32 sP[];
+    __shared__ unsigned long long s_bar;
+    k3_bulk_load(sP, p.tb.pair, K2V3_SMEM_BYTES, &s_bar);
+    const u32 sbase = (u32)__cvta_generic_to_shared(sP);
+
+    const unsigned lane = threadIdx.x & 31;
+    const long total_threads = (long)gridDim.x * blockDim.x;
+    long item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // first game: static assignment
+    bool first = true, exhausted = false;
+    bool have = false;
+    u64 b = 0, keyc = 0;
+    u32 count = 0, n4 = 0, pot0 = 0, limit = 0, rs = 0;
+    long slot = 0;
+    const u32 o0 = p.order[0], o1 = p.order[1], o2 = p.order[2], o3 = p.order[3];
+    const u64 key_off = (u64)(B2048_INIT_DRAWS + p.spawn0 + 1u) * B2048_GOLDEN;  // keyc = key + key_off
+
+    // All 32 lanes stay in the loop until the warp has no game left; dead lanes wait until K2_REFILL_MIN of them can be
+    // refilled together (starting a game costs the whole warp a few hundred instructions).
+    for (;;) {
+        unsigned alive_mask = __ballot_sync(0xffffffffu, have);
+        if (__popc(~alive_mask) >= K2_REFILL_MIN || alive_mask == 0u) {
+            if (!have && !exhausted) {
+                if (!first) {
+                    unsigned m = __activemask();
+                    int leader = __ffs(m) - 1;
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    item = total_threads + (long)base + __popc(m & ((1u << lane) - 1));
+                }
+                first = false;
+                if (item >= p.n) {
+                    exhausted = true;
+                } else {
+                    slot = item;
+                    count = 0;
+                    n4 = 0;
+                    rs = 0;
+                    bool skip = false;
+                    u64 key;
+                    if (p.root_mode) {
+                        long r = item / p.line_count;
+                        int j = p.line_begin + (int)(item - r * p.line_count);
+                        slot = r * p.number + j;
+                        key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
+                        if (!p.rlegal[r]) {
+                            skip = true;
+                        } else {
+                            u32 rs_;
+                            u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs_);  // mcts.py:21
+                            rs = p.rscore[r];
+                            if (countzero(rb) == 0) {
+                                *p.err_flag = 1;
+                                skip = true;
+                            } else {
+                                u32 four;
+                                b = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);  // mcts.py:23
+                            }
+                        }
+                    } else {
+                        key = rng_key(p.seed, p.gid_base + (u64)item);
+                        u64 s0 = p.start ? p.start[item] : 0ULL;
+                        b = s0 ? s0 : init_board(key);  // board.py:205 `if not board`
+                    }
+                    keyc = key + key_off;
+                    if (skip) {
+                        if (p.out_final) p.out_final[slot] = 0;
+                        if (p.out_score) p.out_score[slot] = 0;
+                        if (p.out_moves) p.out_moves[slot] = 0;
+                    } else {
+                        const uint2 st = board_stat(b, p.tb);
+                        pot0 = st.x;
+                        // moves that can neither annihilate (tile sum < 65536) nor leave the pair table (tile sum < 16384)
+                        limit = st.y >= K3_TILESUM_MAX ? 0u : ((K3_TILESUM_MAX - st.y + 3u) >> 2);
+                        have = true;
+                    }
+                }
+            }
+            alive_mask = __ballot_sync(0xffffffffu, have);
+            if (alive_mask == 0u && __all_sync(0xffffffffu, exhausted)) break;
+        }
+        if (!have) continue;
+
+        bool going = k3_step<LUDR>(sbase, b, keyc, count, n4, limit, o0, o1, o2, o3);
+#pragma unroll
+        for (int u = 1; u < K3_UNROLL; u++)
+            if (going) going = k3_step<LUDR>(sbase, b, keyc, count, n4, limit, o0, o1, o2, o3);
+        if (going) continue;
+
+        // ---- game over, or hand-over to the exact path (which also finds a dead board dead) ----------
+        u32 score = board_stat(b, p.tb).x - pot0 - 4u * n4;
+        if (count >= limit) {
+            ExactResult r = finish_exact(p, b, keyc - key_off, count, score);
+            b = r.b;
+            count = r.count;
+            score = r.score;
+            if (r.err) *p.err_flag = 1;
+        }
+        if (p.out_final) p.out_final[slot] = b;
+        if (p.out_score) p.out_score[slot] = score;
+        if (p.out_moves) p.out_moves[slot] = count;
+        if (p.root_mode) {
+            long r = slot / p.number;
+            if (p.out_logsum) {
+                double t = log10((double)score + (double)rs + 1.0);  // mcts.py:31
                 long long q = __double2ll_rn(ldexp(t, 40));
                 atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
             }

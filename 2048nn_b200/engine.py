@@ -278,7 +278,8 @@ class HostPlayout:
 
 
 def set_playout_variant(variant, device=None):
-    """K2 kernel variant: 1 (default) legality-first uniform slide, 0 the L,U,D,R attempt cascade."""
+    """K2 kernel variant: 2 (default) pair table (both slides of a row per lookup), 1 legality-first uniform slide,
+    0 the L,U,D,R attempt cascade."""
     L.check(L.load_library().b2048_set_playout_variant(L.ctx(device), int(variant)))
 
 

@@ -65,8 +65,9 @@ int b2048_num_sms(const b2048_ctx *ctx);
 /* kernels launched through this context since b2048_create (launch accounting of bench.py's gpu_launches) */
 int64_t b2048_launch_count(const b2048_ctx *ctx);
 
-/* Fixed-order playout kernel variant: 1 (default) = legality-first with one uniform table slide per
- * move; 0 = the L,U,D,R attempt cascade.  Both are bit-exact; the switch exists for A/B measurements. */
+/* Fixed-order playout kernel variant: 2 (default) = both slides of a row in one shared-memory word, the four
+ * candidate boards from 8 lookups; 1 = legality table first, then one uniform table slide per move; 0 = the
+ * L,U,D,R attempt cascade.  All are bit-exact; the switch exists for A/B measurements. */
 int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
 
 /* Latency variants of the tensor-core kernels for small launches (results are identical in every mode):

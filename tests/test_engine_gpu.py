@@ -189,10 +189,10 @@ def test_host_playout_pipeline_matches_device_path(eng, orc):
     assert torch.equal(hs2, s.cpu()) and torch.equal(hm2, c.cpu())
 
 
-def test_both_playout_variants_are_bit_exact(eng, orc, eg):
+def test_all_playout_variants_are_bit_exact(eng, orc, eg):
     n = eg["pf_final"].size
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             eng.set_playout_variant(variant)
             f, s, c = eng.playout_fixed(n, int(eg["pf_seed"]), 0)
             assert np.array_equal(host_u64(f), eg["pf_final"]) and np.array_equal(s.cpu().numpy().astype(np.uint64), eg["pf_score"])
@@ -203,7 +203,7 @@ def test_both_playout_variants_are_bit_exact(eng, orc, eg):
                 w = orc.play_order(0, (3, 0, 2, 1), keys[g])
                 assert (int(host_u64(f)[g]), int(s[g].item()), int(c[g].item())) == w
     finally:
-        eng.set_playout_variant(1)
+        eng.set_playout_variant(2)
 
 
 def test_full_size_properties_16m_games(eng):

@@ -5,6 +5,14 @@ import torch
 pkg = importlib.import_module("2048nn_b200")
 eng = pkg.engine
 n = 1 << 24
+if len(sys.argv) > 1:
+    eng.set_playout_variant(int(sys.argv[1]))
+h = torch.empty(n, dtype=torch.int64).pin_memory(); dd = torch.empty(n, dtype=torch.int64, device="cuda")
+for name, (a, b_) in {"H2D": (dd, h), "D2H": (h, dd)}.items():
+    a.copy_(b_, non_blocking=True); torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(); a.copy_(b_, non_blocking=True); t1.record(); torch.cuda.synchronize()
+    print(f"{name} 134 MB pinned: {t0.elapsed_time(t1):.2f} ms = {n * 8 / t0.elapsed_time(t1) / 1e6:.1f} GB/s", flush=True)
 start = eng.init_boards(n, 777, 0)
 h_start = start.cpu().pin_memory()
 out = eng.playout_fixed(n, 1, 0, start=start)

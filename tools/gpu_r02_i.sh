@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_engine_gpu.py -m gpu -q --timeout 150 -x > gpurun_out/r02i_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02i_pytest.log
+tail -5 gpurun_out/r02i_pytest.log
+for l in A B C D E F G; do echo "== lib$l"; B2048_LIB=$PWD/2048nn_b200/exp/lib$l.so timeout 120 python tools/quick_k2.py 2; done 2>&1 | tee gpurun_out/r02i_k2.txt
