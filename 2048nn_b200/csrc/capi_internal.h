@@ -17,7 +17,7 @@ struct b2048_ctx {
     uint32_t *score;
     uint8_t *moved_fwd, *moved_rev, *legal;
     uint2 *rowstat;
-    uint32_t *pair;               // u32[K3_ROWS] fin_fwd | fin_rev << 16 (engine.cuh)
+    uint32_t *pair;               // u32[K3_ROWS] XOR deltas of both slides of a row (engine.cuh)
     std::atomic<int> k2_variant;  // 0 = attempt cascade, 1 = legality-first uniform slide, 2 = pair table (default)
     int main_single_pct;          // main-game launches up to this % of (32 x #SMs) lines in flight run one tile-set per CTA
     std::atomic<int> tc_wide;     // 1 = small tensor-core launches use the 16-warp one-set (latency) kernel variant

@@ -25,7 +25,7 @@ struct Tables {
     const uint32_t *score;
     const uint8_t *legal;  // u8[65536]: bit 0 = row moves toward nibble 0, bit 1 = toward nibble 3
     const uint2 *rowstat;  // [65536] per row: .x = sum (t-1)*2^t ("potential"), .y = sum 2^t (tile sum)
-    const uint32_t *pair;  // u32[K3_ROWS]: fin_fwd | fin_rev << 16 for the rows whose nibble 3 is below 14
+    const uint32_t *pair;  // u32[K3_ROWS]: (fin_fwd ^ row) | (fin_rev ^ row) << 16 for the rows whose nibble 3 is below 14
 };
 // K2 variant 2 keeps `pair` in shared memory: 0xE000 rows x 4 B = 224 KB of the 227 KB a CTA may have.  A row index
 // >= K3_ROWS needs a tile 2^14 or 2^15 in board column 3 / row 3, i.e. a tile sum >= 16384; games hand over to the
@@ -137,7 +137,9 @@ __device__ __forceinline__ u32 rng_word(u64 key, u32 w) {
 // ---------------------------------------------------------------------------------------
 // bit 4k+3 set when nibble k is empty: (h & 7..7) + 7..7 carries into bit 3 of every nonzero nibble (3 instructions,
 // the add can go to the FMA pipe)
-__device__ __forceinline__ u32 empty_mask32_hi(u32 h) { return ~(((h & 0x77777777u) + 0x77777777u) | h) & 0x88888888u; }
+__device__ __forceinline__ u32 empty_mask32_hi(u32 h) {
+    return lop3<0x02>((h & 0x77777777u) + 0x77777777u, h, 0x88888888u);  // ~(a | b) & c in one LOP3
+}
 __device__ __forceinline__ u64 spawn_tile(u64 board, u64 draw, u32 &is_four) {
     u32 lo = lo32(board), hi = hi32(board);
     const u32 zl = empty_mask32_hi(lo), zh = empty_mask32_hi(hi);

@@ -22,7 +22,7 @@ __global__ void build_tables_kernel(uint16_t *fin_fwd, uint16_t *fin_rev, uint32
     moved_rev[r] = fr != r;
     legal[r] = (uint8_t)((ff != r) | ((fr != r) << 1));
     rowstat[r] = make_uint2(potential((u64)r), tile_sum((u64)r));
-    if (r < K3_ROWS) pair[r] = ff | (fr << 16);  // both slides of a row in one word (K2 variant 2)
+    if (r < K3_ROWS) pair[r] = (ff ^ r) | ((fr ^ r) << 16);  // both slides of a row as XOR deltas in one word (K2 variant 2)
     // invariants the playout kernel relies on: equal scores, mirrored finals
     u32 mf, ms;
     row_slide(mirror32(r) & 0xFFFFu, false, mf, ms);
@@ -637,10 +637,10 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
 // ncu on variant 1 (profiles/r02_k2_playout_fixed_ncu.txt): ALU pipe 88 % busy, shared-memory wavefronts 86 % of peak,
 // 174 executed thread-instructions per move -- the kernel is bound by the NUMBER of ALU-pipe instructions and of
 // shared-memory lookups per move.  This variant removes both kinds of work instead of rescheduling it:
-//  * one u32 table entry per row holds BOTH slides (toward nibble 0 in the low half, toward nibble 3 in the high half),
-//    so 8 lookups (4 rows of the board, 4 rows of its transpose) give all four candidate boards: no legality table (legal
-//    <=> candidate != board), no mirror(), no second round of lookups for the chosen direction -- 8 LDS.32 per move
-//    instead of 8 LDS.U8 + 4 LDS.U16;
+//  * one u32 table entry per row holds BOTH slides as XOR deltas (slide toward nibble 0 ^ row in the low half, toward
+//    nibble 3 in the high half), so 8 lookups (4 rows of the board, 4 rows of its transpose) give all four candidate
+//    boards: no legality table (a direction is legal iff the OR of its four deltas is nonzero), no mirror(), no second
+//    round of lookups for the chosen direction -- 8 LDS.32 per move instead of 8 LDS.U8 + 4 LDS.U16;
 //  * the table covers rows < K3_ROWS (224 KB of shared memory, filled by cp.async.bulk); a larger row index needs a tile
 //    sum >= 16384, and a game hands over to the exact global-table path before that is possible (the hand-over that
 //    already guards the 32768+32768 annihilation, so it costs nothing per move);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
 // ---------------------------------------------------------------------------------------
 #define K2V3_SMEM_BYTES (K3_ROWS * 4)
 #ifndef K3_UNROLL
-#define K3_UNROLL 4
+#define K3_UNROLL 8
 #endif
 
 __device__ __forceinline__ void k3_bulk_load(void *smem_dst, const void *gsrc, u32 bytes, unsigned long long *bar) {
@@ -681,7 +681,7 @@ __device__ __forceinline__ void k3_bulk_load(void *smem_dst, const void *gsrc, u
 
 // byte offsets of the two rows of a 32-bit half in the pair table
 __device__ __forceinline__ u32 k3_off_lo(u32 h) { return (h << 2) & 0x3FFFCu; }
-__device__ __forceinline__ u32 k3_off_hi(u32 h) { return (h >> 14) & 0x3FFFCu; }  // (IMAD.HI instead of SHF measured slower)
+__device__ __forceinline__ u32 k3_off_hi(u32 h) { return (h >> 14) & 0x3FFFCu; }  // (IMAD.HI or PRMT+IMAD instead of SHF+LOP3: measured slower / same)
 __device__ __forceinline__ u32 k3_ld(u32 smem_base, u32 off) {
     u32 v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_base + off));  // read-only after k3_bulk_load
@@ -700,27 +700,24 @@ __device__ __forceinline__ bool k3_step(u32 sbase, u64 &b, u64 keyc, u32 &count,
     const u32 e2 = k3_ld(sbase, k3_off_lo(hi)), e3 = k3_ld(sbase, k3_off_hi(hi));
     const u32 c0 = k3_ld(sbase, k3_off_lo(tlo)), c1 = k3_ld(sbase, k3_off_hi(tlo));
     const u32 c2 = k3_ld(sbase, k3_off_lo(thi)), c3 = k3_ld(sbase, k3_off_hi(thi));
-    const u32 Ll = __byte_perm(e0, e1, 0x5410), Lh = __byte_perm(e2, e3, 0x5410);  // Left  (rows of b, toward nibble 0)
-    const u32 Rl = __byte_perm(e0, e1, 0x7632), Rh = __byte_perm(e2, e3, 0x7632);  // Right
-    const u32 Ul = __byte_perm(c0, c1, 0x5410), Uh = __byte_perm(c2, c3, 0x5410);  // Up    (rows of bt)
-    const u32 Dl = __byte_perm(c0, c1, 0x7632), Dh = __byte_perm(c2, c3, 0x7632);  // Down
-    const bool lL = (Ll != lo) | (Lh != hi), lR = (Rl != lo) | (Rh != hi);
-    const bool lU = (Ul != tlo) | (Uh != thi), lD = (Dl != tlo) | (Dh != thi);
-    if (!(lL | lR | lU | lD)) return false;
-    u32 vl, vh, hl, hh;
-    bool vert;
+    // entries hold (slide ^ row): a direction is legal iff some row's delta is nonzero
+    const u32 he = e0 | e1 | e2 | e3, ve = c0 | c1 | c2 | c3;
+    const bool lL = (he & 0xFFFFu) != 0, lR = (he & 0xFFFF0000u) != 0;
+    const bool lU = (ve & 0xFFFFu) != 0, lD = (ve & 0xFFFF0000u) != 0;
+    if ((he | ve) == 0) return false;
+    bool hfwd, vfwd, vert;
     if (LUDR) {  // Left, else Up, else Down, else Right
-        vl = lU ? Ul : Dl, vh = lU ? Uh : Dh;
-        hl = lL ? Ll : Rl, hh = lL ? Lh : Rh;
+        hfwd = lL, vfwd = lU;
         vert = !lL & (lU | lD);
     } else {
         const u32 mask = (u32)lL | ((u32)lU << 1) | ((u32)lR << 2) | ((u32)lD << 3);
         const u32 d = ((mask >> o0) & 1u) ? o0 : ((mask >> o1) & 1u) ? o1 : ((mask >> o2) & 1u) ? o2 : o3;
-        const bool fwd = (d & 2u) == 0;
-        vl = fwd ? Ul : Dl, vh = fwd ? Uh : Dh;
-        hl = fwd ? Ll : Rl, hh = fwd ? Lh : Rh;
+        hfwd = vfwd = (d & 2u) == 0;
         vert = (d & 1u) != 0;
     }
+    const u32 hsel = hfwd ? 0x5410u : 0x7632u, vsel = vfwd ? 0x5410u : 0x7632u;
+    const u32 hl = lo ^ __byte_perm(e0, e1, hsel), hh = hi ^ __byte_perm(e2, e3, hsel);
+    const u32 vl = tlo ^ __byte_perm(c0, c1, vsel), vh = thi ^ __byte_perm(c2, c3, vsel);
     const u64 tv = transpose(pack64(vl, vh));
     const u64 y = vert ? tv : pack64(hl, hh);
     u32 four;

@@ -538,6 +538,15 @@ def main():
     hp = eng.HostPlayout(n)
     h_start = start.cpu().pin_memory()
     hp(h_start, 3000, gid_base)
+    # the box's PCIe rates for these very buffers (reported next to e2e: a slow host link shows up here, not in the kernel)
+    pcie = {}
+    for name, (dst, src) in {"h2d_gbs": (hp.d_start, h_start), "d2h_gbs": (hp.h_out[1], hp.d_out[1])}.items():
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        pcie[name] = src.numel() * src.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -594,12 +603,23 @@ def main():
     hbm_bytes = 24.0 * n * args.steps  # 8 B start + 16 B results per game
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same size only)
     tpath = os.path.join(ROOT, "profiles", "r02_k2_traffic_16m.json")
-    measured_instr = None
+    measured_instr, executed = None, None
     if os.path.exists(tpath):
         tinfo = json.load(open(tpath))
         measured_instr = tinfo.get("thread_instr_per_move")
         if tinfo.get("games") == n:
             traffic = tinfo["traffic_bytes_per_launch"]
+        if measured_instr:
+            # the executed view: what the kernel issues, against the issue slots and against the ALU pipe that binds it
+            executed = {"kernel": tinfo.get("kernel"), "thread_instr_per_move": measured_instr,
+                        "issue_frac_at_max_clock": per_gpu_moves_per_s * measured_instr / issue_peak,
+                        # the binding pipe: ALU-pipe lane-slots per move (ncu) x live moves/s vs 16 lanes x 4 x SMs x max clock
+                        "alu_pipe_frac_at_max_clock": (per_gpu_moves_per_s * tinfo["alu_pipe_lane_slots_per_move"] / (issue_peak / 2)
+                                                       if tinfo.get("alu_pipe_lane_slots_per_move") else None),
+                        "ncu_alu_pipe_active_pct": tinfo.get("alu_pipe_active_pct"),
+                        "ncu_issue_active_pct": tinfo.get("issue_active_pct"),
+                        "ncu_shared_wavefronts_pct_of_peak": tinfo.get("shared_wavefronts_pct_of_peak"),
+                        "source": "committed ncu capture (profiles/r02_k2_traffic_16m.json), not measured in this run"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -609,15 +629,17 @@ def main():
                    "parallelism": f"games sharded over {world} GPU(s), no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps, "pcie_probe": pcie},
         "gpu_launches": main_launches,
         "roofline": {"bound": "sm_issue", "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
                      "frac": achieved / issue_peak, "traffic": traffic,
                      "traffic_source": "committed ncu capture profiles/r02_k2_traffic_16m.json (same size), not measured in this run",
                      "measured_thread_instr_per_move": measured_instr,
-                     "note": "algorithmic 250 thread-instr/move (SURVEY 8d) x moves/s vs %d SM x 4 x 32 x %.0f MHz (%s clocks); the kernel "
-                             "EXECUTES 174 thread-instr/move (ncu), 62 %% of them on the half-rate ALU pipe (88 %% busy, the binder; "
-                             "shared-memory wavefronts 86 %%); HBM sees only %.1f GB/s of %.0f"
+                     "executed": executed,
+                     "note": "frac = algorithmic 250 thread-instr/move (SURVEY 8d: the reference-shaped attempt cascade) x moves/s vs %d SM x 4 x 32 x "
+                             "%.0f MHz (%s clocks); it exceeds 1 because the pair-table kernel does less work per move than that model "
+                             "(`executed`: thread-instr/move and pipe utilisation from the committed ncu capture; the ALU pipe is the binder, "
+                             "shared-memory wavefronts second); HBM sees only %.1f GB/s of %.0f"
                              % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
                                 peaks["hbm_gbs"])},
     }
