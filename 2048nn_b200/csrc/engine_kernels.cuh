@@ -644,6 +644,8 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
 //  * the table covers rows < K3_ROWS (224 KB of shared memory, filled by cp.async.bulk); a larger row index needs a tile
 //    sum >= 16384, and a game hands over to the exact global-table path before that is possible (the hand-over that
 //    already guards the 32768+32768 annihilation, so it costs nothing per move);
+//  * games are prepared 32 at a time by the whole warp (a pool of one stash entry per lane, handed out by shuffles) and
+//    finished games are written out in batches, so the divergent start / finish code runs at full lane occupancy;
 //  * K3_UNROLL moves per pass of the outer loop (the refill vote is paid once per pass), the spawn's draw counter folded
 //    into the key (two IMADs per draw), transposes as 4-instruction delta swaps, a 3-instruction empty mask.
 // Bit-exact with variants 0 and 1 (tests/test_engine_gpu.py).
@@ -651,6 +653,9 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel2(const PlayParam
 #define K2V3_SMEM_BYTES (K3_ROWS * 4)
 #ifndef K3_UNROLL
 #define K3_UNROLL 8
+#endif
+#ifndef K3_REFILL_MIN
+#define K3_REFILL_MIN 2
 #endif
 
 __device__ __forceinline__ void k3_bulk_load(void *smem_dst, const void *gsrc, u32 bytes, unsigned long long *bar) {
@@ -736,79 +741,135 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel3(const PlayParam
 
     const unsigned lane = threadIdx.x & 31;
     const long total_threads = (long)gridDim.x * blockDim.x;
-    long item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // first game: static assignment
-    bool first = true, exhausted = false;
-    bool have = false;
+    bool first = true;
+    bool have = false, fin = false;  // fin: the lane holds a finished game whose results are not written yet
     u64 b = 0, keyc = 0;
     u32 count = 0, n4 = 0, pot0 = 0, limit = 0, rs = 0;
     long slot = 0;
+    u64 sb = 0, skeyc = 0;  // this lane's entry of the warp's pool of prepared games
+    u32 spot0 = 0, slimit = 0, srs = 0;
+    long sslot = 0;
+    int pool = 0;            // warp-uniform: entries 0 .. pool-1 of the pool are still to be handed out
+    bool pool_done = false;  // warp-uniform: the launch has no further games
     const u32 o0 = p.order[0], o1 = p.order[1], o2 = p.order[2], o3 = p.order[3];
     const u64 key_off = (u64)(B2048_INIT_DRAWS + p.spawn0 + 1u) * B2048_GOLDEN;  // keyc = key + key_off
 
-    // All 32 lanes stay in the loop until the warp has no game left; dead lanes wait until K2_REFILL_MIN of them can be
-    // refilled together (starting a game costs the whole warp a few hundred instructions).
+    // All 32 lanes stay in the loop until the warp has no game left; dead lanes wait until K3_REFILL_MIN of them can write
+    // their results and take a new game together.  New games come from a per-warp pool of 32 prepared games (one stash
+    // entry per lane, in registers): preparing a game (key, start board, potential, move budget: a few hundred
+    // instructions and four L2 loads) is done by all 32 lanes at once whenever the pool runs dry, not by the few dead lanes.
     for (;;) {
         unsigned alive_mask = __ballot_sync(0xffffffffu, have);
-        if (__popc(~alive_mask) >= K2_REFILL_MIN || alive_mask == 0u) {
-            if (!have && !exhausted) {
-                if (!first) {
-                    unsigned m = __activemask();
-                    int leader = __ffs(m) - 1;
-                    unsigned long long base = 0;
-                    if ((int)lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(m));
-                    base = __shfl_sync(m, base, leader);
-                    item = total_threads + (long)base + __popc(m & ((1u << lane) - 1));
+        if (__popc(~alive_mask) >= K3_REFILL_MIN || alive_mask == 0u) {
+            if (fin) {
+                // ---- game over, or hand-over to the exact path (which also finds a dead board dead) ----------
+                u32 score = board_stat(b, p.tb).x - pot0 - 4u * n4;
+                if (count >= limit) {
+                    ExactResult r = finish_exact(p, b, keyc - key_off, count, score);
+                    b = r.b;
+                    count = r.count;
+                    score = r.score;
+                    if (r.err) *p.err_flag = 1;
                 }
-                first = false;
-                if (item >= p.n) {
-                    exhausted = true;
-                } else {
-                    slot = item;
-                    count = 0;
-                    n4 = 0;
-                    rs = 0;
-                    bool skip = false;
-                    u64 key;
-                    if (p.root_mode) {
-                        long r = item / p.line_count;
-                        int j = p.line_begin + (int)(item - r * p.line_count);
-                        slot = r * p.number + j;
-                        key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
-                        if (!p.rlegal[r]) {
-                            skip = true;
-                        } else {
-                            u32 rs_;
-                            u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs_);  // mcts.py:21
-                            rs = p.rscore[r];
-                            if (countzero(rb) == 0) {
-                                *p.err_flag = 1;
+                if (p.out_final) p.out_final[slot] = b;
+                if (p.out_score) p.out_score[slot] = score;
+                if (p.out_moves) p.out_moves[slot] = count;
+                if (p.root_mode) {
+                    long r = slot / p.number;
+                    if (p.out_logsum) {
+                        double t = log10((double)score + (double)rs + 1.0);  // mcts.py:31
+                        long long q = __double2ll_rn(ldexp(t, 40));
+                        atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
+                    }
+                    if (p.out_count) atomicAdd(p.out_count + r, 1);
+                    if (p.out_minmov) atomicMin(p.out_minmov + r, (int)count);
+                }
+                fin = false;
+            }
+            // Hand out prepared games; whenever the pool runs dry ALL 32 lanes prepare one game each (key, start board,
+            // potential, move budget) at full lane occupancy, instead of the few dead lanes preparing their own.
+            for (;;) {
+                const unsigned need = __ballot_sync(0xffffffffu, !have);
+                if (need == 0u) break;
+                if (pool == 0) {
+                    if (pool_done) break;
+                    long item;
+                    if (first) {
+                        item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // first games: static assignment
+                        first = false;
+                    } else {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(p.counter, 32ULL);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        item = total_threads + (long)base + lane;
+                    }
+                    const bool valid = item < p.n;  // items grow with the lane: the valid lanes are 0 .. V-1
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    if (vm != 0xffffffffu) pool_done = true;  // the launch has no further games
+                    if (vm == 0u) break;
+                    sb = 0;  // 0 = no game in this stash entry (skipped root move)
+                    if (valid) {
+                        sslot = item;
+                        srs = 0;
+                        bool skip = false;
+                        u64 key, nb = 0;
+                        if (p.root_mode) {
+                            long r = item / p.line_count;
+                            int j = p.line_begin + (int)(item - r * p.line_count);
+                            sslot = r * p.number + j;
+                            key = rng_key(p.seed, (p.gid_base + (u64)r) * (u64)p.number + (u64)j);
+                            if (!p.rlegal[r]) {
                                 skip = true;
                             } else {
-                                u32 four;
-                                b = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);  // mcts.py:23
+                                u32 rs_;
+                                u64 rb = move_exact(p.origins[r >> 2], (int)(r & 3), p.tb, rs_);  // mcts.py:21
+                                srs = p.rscore[r];
+                                if (countzero(rb) == 0) {
+                                    *p.err_flag = 1;
+                                    skip = true;
+                                } else {
+                                    u32 four;
+                                    nb = spawn_tile(rb, rng_draw(key, B2048_INIT_DRAWS), four);  // mcts.py:23
+                                }
                             }
+                        } else {
+                            key = rng_key(p.seed, p.gid_base + (u64)item);
+                            u64 s0 = p.start ? p.start[item] : 0ULL;
+                            nb = s0 ? s0 : init_board(key);  // board.py:205 `if not board`
                         }
-                    } else {
-                        key = rng_key(p.seed, p.gid_base + (u64)item);
-                        u64 s0 = p.start ? p.start[item] : 0ULL;
-                        b = s0 ? s0 : init_board(key);  // board.py:205 `if not board`
+                        skeyc = key + key_off;
+                        if (skip) {
+                            if (p.out_final) p.out_final[sslot] = 0;
+                            if (p.out_score) p.out_score[sslot] = 0;
+                            if (p.out_moves) p.out_moves[sslot] = 0;
+                        } else {
+                            const uint2 st = board_stat(nb, p.tb);
+                            spot0 = st.x;
+                            // moves that can neither annihilate (tile sum < 65536) nor leave the pair table (tile sum < 16384)
+                            slimit = st.y >= K3_TILESUM_MAX ? 0u : ((K3_TILESUM_MAX - st.y + 3u) >> 2);
+                            sb = nb;
+                        }
                     }
-                    keyc = key + key_off;
-                    if (skip) {
-                        if (p.out_final) p.out_final[slot] = 0;
-                        if (p.out_score) p.out_score[slot] = 0;
-                        if (p.out_moves) p.out_moves[slot] = 0;
-                    } else {
-                        const uint2 st = board_stat(b, p.tb);
-                        pot0 = st.x;
-                        // moves that can neither annihilate (tile sum < 65536) nor leave the pair table (tile sum < 16384)
-                        limit = st.y >= K3_TILESUM_MAX ? 0u : ((K3_TILESUM_MAX - st.y + 3u) >> 2);
-                        have = true;
-                    }
+                    pool = __popc(vm);
                 }
+                // the j-th lane in need takes stash entry pool-1-j
+                const int src = pool - 1 - __popc(need & ((1u << lane) - 1u));
+                const int sl = src < 0 ? 0 : src;
+                const u64 tb_ = __shfl_sync(0xffffffffu, sb, sl), tk = __shfl_sync(0xffffffffu, skeyc, sl);
+                const u32 tp = __shfl_sync(0xffffffffu, spot0, sl), tl = __shfl_sync(0xffffffffu, slimit, sl);
+                const u32 tr = __shfl_sync(0xffffffffu, srs, sl);
+                const long tsl = __shfl_sync(0xffffffffu, sslot, sl);
+                if (!have && src >= 0 && tb_ != 0) {
+                    b = tb_, keyc = tk, pot0 = tp, limit = tl, rs = tr, slot = tsl;
+                    count = 0, n4 = 0;
+                    have = true;
+                }
+                const int taken = __popc(need);
+                pool = pool > taken ? pool - taken : 0;
             }
             alive_mask = __ballot_sync(0xffffffffu, have);
-            if (alive_mask == 0u && __all_sync(0xffffffffu, exhausted)) break;
+            if (alive_mask == 0u && pool_done && pool == 0) break;
+
         }
         if (!have) continue;
 
@@ -817,30 +878,10 @@ __global__ void __launch_bounds__(1024, 1) playout_fixed_kernel3(const PlayParam
         for (int u = 1; u < K3_UNROLL; u++)
             if (going) going = k3_step<LUDR>(sbase, b, keyc, count, n4, limit, o0, o1, o2, o3);
         if (going) continue;
-
-        // ---- game over, or hand-over to the exact path (which also finds a dead board dead) ----------
-        u32 score = board_stat(b, p.tb).x - pot0 - 4u * n4;
-        if (count >= limit) {
-            ExactResult r = finish_exact(p, b, keyc - key_off, count, score);
-            b = r.b;
-            count = r.count;
-            score = r.score;
-            if (r.err) *p.err_flag = 1;
-        }
-        if (p.out_final) p.out_final[slot] = b;
-        if (p.out_score) p.out_score[slot] = score;
-        if (p.out_moves) p.out_moves[slot] = count;
-        if (p.root_mode) {
-            long r = slot / p.number;
-            if (p.out_logsum) {
-                double t = log10((double)score + (double)rs + 1.0);  // mcts.py:31
-                long long q = __double2ll_rn(ldexp(t, 40));
-                atomicAdd(reinterpret_cast<unsigned long long *>(p.out_logsum + r), (unsigned long long)q);
-            }
-            if (p.out_count) atomicAdd(p.out_count + r, 1);
-            if (p.out_minmov) atomicMin(p.out_minmov + r, (int)count);
-        }
+        // the game is over here (or must be handed over to the exact path): its results are written in the batched block
+        // above, together with the other finished lanes' and the refill
         have = false;
+        fin = true;
     }
 }
 

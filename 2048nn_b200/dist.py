@@ -74,18 +74,35 @@ def embed_partial(part, G, o0, o1):
     return out
 
 
-def allreduce_root_stats(stats, group=None):
+def allreduce_root_stats(stats, group=None, async_op=False):
     """In-place allreduce of a partial-statistics dict (keys present among logsum/count: SUM;
-    minmov: MIN).  No-op without an initialised process group."""
+    minmov: MIN).  No-op without an initialised process group.
+
+    async_op=True only ENQUEUES the collectives (they run on the communication stream once this rank's kernel is
+    done) and returns at once, so the caller's stream can start the next root evaluation without waiting for the
+    slowest rank: the statistics are valid after wait_root_stats(stats).  Independent evaluations pipelined this way
+    pay the load imbalance between ranks once per pipeline instead of once per evaluation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats
+    pending = []
     if "logsum" in stats and stats["logsum"] is not None:
         packed = torch.stack([stats["logsum"], stats["count"].to(torch.int64)])  # one collective for both
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-        stats["logsum"].copy_(packed[0])
-        stats["count"].copy_(packed[1].to(stats["count"].dtype))
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        pending.append((work, packed))
     if "minmov" in stats and stats["minmov"] is not None:
-        dist.all_reduce(stats["minmov"], op=dist.ReduceOp.MIN, group=group)
+        pending.append((dist.all_reduce(stats["minmov"], op=dist.ReduceOp.MIN, group=group, async_op=async_op), None))
+    stats["_pending"] = pending
+    return stats if async_op else wait_root_stats(stats)
+
+
+def wait_root_stats(stats):
+    """Complete the collectives enqueued by allreduce_root_stats (the current stream waits for them) and unpack."""
+    for work, packed in stats.pop("_pending", []):
+        if work is not None:
+            work.wait()
+        if packed is not None:
+            stats["logsum"].copy_(packed[0])
+            stats["count"].copy_(packed[1].to(stats["count"].dtype))
     return stats
 
 
@@ -103,7 +120,7 @@ def min_from_stats(legal, minmov, illegal_value=0):
 
 
 # ---- sharded root evaluations on the GPU --------------------------------------------------------
-def _sharded(run, origins, number, eval_id_base, group):
+def _sharded(run, origins, number, eval_id_base, group, async_reduce=False):
     """run(origins, eval_id_base, line_begin, line_end) -> statistics dict of those origins / lines."""
     rank, ws = world()
     G = origins.numel()
@@ -121,7 +138,7 @@ def _sharded(run, origins, number, eval_id_base, group):
         r.update(embed_partial(part, G, o0, o1))
         if part.get("total_moves") is not None:
             r["total_moves"] = part["total_moves"]
-    allreduce_root_stats(r, group)
+    allreduce_root_stats(r, group, async_op=async_reduce)
     # r["total_moves"] (throughput accounting) stays THIS RANK's count: callers sum it over ranks once, at the end of
     # a run, instead of paying a second collective per root evaluation (sum_over_ranks below)
     return r
@@ -146,12 +163,20 @@ def mcts_fixed_sharded(origins, number, seed, eval_id_base=0, group=None):
     return r
 
 
-def mcts_nn_sharded(blob, precision, origins, number, seed, eval_id_base=0, group=None):
+def mcts_nn_sharded(blob, precision, origins, number, seed, eval_id_base=0, group=None, async_reduce=False):
     """NN-policy root search (mcts_nn.py:4-43) sharded over the process group (shard_plan).  With line sharding the
-    early stop uses each rank's local minimum; the allreduce(MIN) restores the global one."""
+    early stop uses each rank's local minimum; the allreduce(MIN) restores the global one.
+    async_reduce=True returns as soon as this rank's launch and the collective are enqueued; call
+    mcts_nn_finish(r) before reading r["minmov"] / r["min"] (pipelining of independent evaluations)."""
     from . import engine
 
     r = _sharded(lambda o, e, b, l: engine.mcts_nn_lines(blob, precision, o, number, seed, e, b, l),
-                 origins, number, eval_id_base, group)
+                 origins, number, eval_id_base, group, async_reduce)
+    return r if async_reduce else mcts_nn_finish(r)
+
+
+def mcts_nn_finish(r):
+    """Second half of mcts_nn_sharded(async_reduce=True): wait for the exchange, derive the values."""
+    wait_root_stats(r)
     r["min"] = min_from_stats(r["legal"], r["minmov"])
     return r

@@ -323,9 +323,15 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     moves = torch.zeros(1, dtype=torch.int64, device="cuda")
     l0 = lc()
     e0.record()
+    inflight = []
     for k in range(args.steps):
-        r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G)
+        # independent evaluations are pipelined: a rank starts evaluation k+1 while the [G,4] MIN exchange of evaluation k
+        # waits for the slowest rank (dist.allreduce_root_stats async_op); every exchange completes inside the timed region
+        r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G, async_reduce=True)
         moves += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
+        inflight.append(r)
+    for r in inflight:
+        d.mcts_nn_finish(r)
     e1.record()
     barrier()
     launches = lc() - l0

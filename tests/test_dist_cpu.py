@@ -67,6 +67,14 @@ def _worker(rank, world_size, port, q):
     plan = d.shard_plan(len(origins), number, rank, world_size)
     r = d._sharded(run, t_orig, number, 0, None)
     q.put((10 + rank, plan, r["logsum"].numpy().copy(), r["count"].numpy().copy(), r["minmov"].numpy().copy(), int(r["total_moves"])))
+    # pipelined evaluations: three exchanges enqueued (async_op) before the first is waited for -- same statistics
+    pend = [d._sharded(run, t_orig, number, 0, None, async_reduce=True) for _ in range(3)]
+    same = True
+    for pr in pend:
+        assert "_pending" in pr
+        d.wait_root_stats(pr)
+        same &= bool(torch.equal(pr["logsum"], r["logsum"]) and torch.equal(pr["count"], r["count"]) and torch.equal(pr["minmov"], r["minmov"]))
+    q.put((20 + rank, same))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -89,12 +97,13 @@ def test_allreduce_root_stats_world2(orc):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(4)]
+    got = [q.get(timeout=120) for _ in range(6)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     got.sort(key=lambda t: t[0])
-    out, by_origin = got[:2], got[2:]
+    out, by_origin, piped = got[:2], got[2:4], got[4:]
+    assert all(p[1] for p in piped)  # async (pipelined) exchanges give the statistics of the blocking ones
     assert out[0][1] == (0, 4) and out[1][1] == (4, 7)
     # every rank holds the same reduced statistics ...
     for k in range(2, 6):

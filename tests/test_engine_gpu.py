@@ -143,6 +143,39 @@ def test_playout_other_orders_and_high_tiles(eng, orc):
                 assert (int(fh[g]), int(sh[g]), int(ch[g])) == (w[0], w[1] & 0xFFFFFFFF, w[2]), (g, hex(starts[g]))
 
 
+def test_playout_hands_over_at_the_pair_table_limit(eng, orc):
+    """K2 variant 2 keeps only the rows < 0xE000 in shared memory and hands a game over to the exact global-table
+    path before its tile sum can reach 16384.  Start boards whose tile sum is just below that bound make games cross
+    it in mid-play (a few moves on the table path, the rest on the exact path); boards at and above it start on the
+    exact path.  Every variant must still agree with the oracle move for move (final board, score, move count)."""
+    rs = np.random.RandomState(11)
+    starts = []
+    for _ in range(1500):
+        # 8192 + 4096 + ... + 128 (+64, +32 ...) in random cells: tile sums 16256 .. 16382
+        exps = [13, 12, 11, 10, 9, 8, 7] + list(rs.choice([6, 5, 4, 3, 2, 1, 0], size=rs.randint(0, 6), replace=False))
+        cells = rs.permutation(16)[:len(exps)]
+        b = 0
+        for c, e in zip(cells, exps):
+            b |= int(e) << (4 * int(c))
+        starts.append(b)
+    starts = np.array(starts, np.uint64)
+    try:
+        for variant in (1, 2):
+            eng.set_playout_variant(variant)
+            f, s, c = eng.playout_fixed(starts.size, 21, 0, start=dev_boards(starts))
+            fh, sh, ch = host_u64(f), s.cpu().numpy().view(np.uint32), c.cpu().numpy().view(np.uint32)
+            crossed = 0
+            for g, st in enumerate(starts.tolist()):
+                w = orc.play_order(st, (0, 1, 3, 2), orc.rng_key(21, g))
+                assert (int(fh[g]), int(sh[g]), int(ch[g])) == (w[0], w[1] & 0xFFFFFFFF, w[2]), (variant, g, hex(st))
+                ts0 = sum(1 << ((st >> (4 * k)) & 15) for k in range(16) if (st >> (4 * k)) & 15)
+                limit = (16384 - ts0 + 3) // 4  # moves the kernel makes on the table path (engine_kernels.cuh)
+                crossed += 0 < limit <= w[2]
+            assert crossed > 300  # the hand-over in mid-game is really exercised
+    finally:
+        eng.set_playout_variant(2)
+
+
 def test_mcts_fixed_lines(eng, orc, eg):
     number, seed = int(eg["mc_number"]), int(eg["mc_seed"])
     origins = eg["mc_origins"]
