@@ -4,6 +4,7 @@ Boards are torch.int64 tensors holding the uint64 bit pattern (nibble k = cell (
 Each function names the reference code it replaces (file:line in fqjin/2048NN).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -255,25 +256,35 @@ class HostPlayout:
             st.wait_stream(cur)
         o = (C.c_uint8 * 4)(*[int(x) & 3 for x in order])
         lib, ctx = L.load_library(), L.ctx(self.device)
+        trace = [] if os.environ.get("B2048_E2E_TRACE") else None  # tools/e2e_diag.py: per-chunk event times
         for i, (b, e) in enumerate(self.bounds):
             s_run = self.s_runs[i & 1]
             with torch.cuda.stream(self.s_in):
+                if trace is not None:
+                    t_in0 = torch.cuda.Event(enable_timing=True); t_in0.record()
                 self.d_start[b:e].copy_(h_start[b:e], non_blocking=True)
-                ev_in = self.s_in.record_event()
+                ev_in = self.s_in.record_event(torch.cuda.Event(enable_timing=True) if trace is not None else None)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in)
+                if trace is not None:
+                    t_run0 = torch.cuda.Event(enable_timing=True); t_run0.record()
                 f = self.d_out[0][b:e] if self.want_final else None
                 L.check(lib.b2048_playout_fixed(ctx, L.ptr(self.d_start[b:e]), o, seed, gid_base + b, 0, L.ptr(f),
                                                 L.ptr(self.d_out[1][b:e]), L.ptr(self.d_out[2][b:e]), e - b,
                                                 C.c_void_p(s_run.cuda_stream)))
-                ev_run = s_run.record_event()
+                ev_run = s_run.record_event(torch.cuda.Event(enable_timing=True) if trace is not None else None)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_run)
                 for h, d in zip(self.h_out, self.d_out):
                     if h is not None:
                         h[b:e].copy_(d[b:e], non_blocking=True)
+                if trace is not None:
+                    t_out1 = torch.cuda.Event(enable_timing=True); t_out1.record()
+                    trace.append((t_in0, ev_in, t_run0, ev_run, t_out1))
         cur.wait_stream(self.s_out)
         self.s_out.synchronize()
+        if trace is not None:
+            self.last_events = trace
         return self.h_out
 
 

@@ -277,19 +277,24 @@ def main_games_block(pkg, blob, G_total, number, main_steps, steps, warmup, seed
         hm = torch.empty(1, dtype=torch.int64).pin_memory()
         h2d = n_local * 8
         d2h = hb.numel() * 8 + hr.numel() * 4 + hs.numel() * 8 + 8
+    def e2e_step(seed):
+        d_start.copy_(h_start, non_blocking=True)
+        r = play(seed, starts=d_start)
+        hb.copy_(r["boards"], non_blocking=True)
+        hr.copy_(r["results"], non_blocking=True)
+        hs.copy_(torch.stack([r["final"], r["score"], r["steps"].to(torch.int64)]), non_blocking=True)
+        hm.copy_(r["total_moves"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(hm[0]) + 0 * int(hs[1, 0])  # the step's results, read on the host
+
+    if n_local:
+        e2e_step(seed0 + 199)  # untimed: the first use of the copy / stack / cast kernels loads them
     barrier()
     log("main games: end-to-end region")
     t0.record()
     for k in range(steps):
         if n_local:
-            d_start.copy_(h_start, non_blocking=True)
-            r = play(seed0 + 200 + k, starts=d_start)
-            hb.copy_(r["boards"], non_blocking=True)
-            hr.copy_(r["results"], non_blocking=True)
-            hs.copy_(torch.stack([r["final"], r["score"], r["steps"].to(torch.int64)]), non_blocking=True)
-            hm.copy_(r["total_moves"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            e2e_moves += int(hm[0]) + 0 * int(hs[1, 0])  # the step's results, read on the host
+            e2e_moves += e2e_step(seed0 + 200 + k)
     t1.record()
     barrier()
     return {"ms": e0.elapsed_time(e1), "e2e_ms": t0.elapsed_time(t1), "moves": float(moves.item()), "mains": float(mains.item()),
@@ -341,16 +346,20 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     h_res = torch.empty((G, 4), dtype=torch.int64).pin_memory()
     d_orig = torch.empty_like(origins)
     e2e_moves = torch.zeros(1, dtype=torch.int64, device="cuda")
+    def e2e_step(k):
+        d_orig.copy_(h_orig, non_blocking=True)
+        r = d.mcts_nn_sharded(blob, "fp16", d_orig, number, 300 + k, k * G)
+        h_res.copy_(r["min"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = int(h_res[0, 0])  # host read of the step's result
+        return r["total_moves"]
+
+    e2e_step(-1)  # untimed: first use of the copies
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for k in range(args.steps):
-        d_orig.copy_(h_orig, non_blocking=True)
-        r = d.mcts_nn_sharded(blob, "fp16", d_orig, number, 300 + k, k * G)
-        h_res.copy_(r["min"], non_blocking=True)
-        e2e_moves += r["total_moves"]
-        torch.cuda.current_stream().synchronize()
-        _ = int(h_res[0, 0])  # host read of the step's result
+        e2e_moves += e2e_step(k)
     t1.record()
     barrier()
     d.sum_over_ranks(moves)
@@ -543,7 +552,9 @@ def main():
     # ---- end to end through the host-buffer API: H2D of start boards + D2H of results ------
     hp = eng.HostPlayout(n)
     h_start = start.cpu().pin_memory()
-    hp(h_start, 3000, gid_base)
+    for w in range(max(3, args.warmup)):  # whole steps, metric read included (its first use loads a reduction kernel: 1-70 ms)
+        hp(h_start, 3000 + w, gid_base)
+        _ = int(hp.d_out[2].sum().item())
     # the box's PCIe rates for these very buffers (reported next to e2e: a slow host link shows up here, not in the kernel)
     pcie = {}
     for name, (dst, src) in {"h2d_gbs": (hp.d_start, h_start), "d2h_gbs": (hp.h_out[1], hp.d_out[1])}.items():
@@ -558,12 +569,29 @@ def main():
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     e2e_moves = 0
+    host_t = []
     for k in range(args.steps):
+        h0 = time.perf_counter()
         _, hs, hm = hp(h_start, 4000 + k, gid_base)  # host arrays: score + move count of every game
+        h1 = time.perf_counter()
         e2e_moves += int(hp.d_out[2].sum().item()) + 0 * int(hm[-1])  # the step's metric, read on the host
+        host_t.append((h1 - h0, time.perf_counter() - h1))
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
+    if os.environ.get("B2048_E2E_TRACE"):
+        mine = "rank %d: e2e %.1f ms/step, pcie %s, host ms per step (HostPlayout call + metric read): %s" % (
+            rank, e2e_ms / args.steps, {k: round(v, 1) for k, v in pcie.items()}, " ".join("%.1f+%.1f" % (a * 1e3, b * 1e3) for a, b in host_t))
+        every = [mine]
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, mine)
+        for ln in every:
+            log(ln)
+    if getattr(hp, "last_events", None):  # B2048_E2E_TRACE=1: per-chunk event times of the last step (diagnostics)
+        base = hp.last_events[0][0]
+        log("e2e trace (ms from the step's first copy): " + " ".join(
+            "c%d[in %.1f-%.1f run %.1f-%.1f out -%.1f]" % ((i,) + tuple(base.elapsed_time(x) for x in ev)) for i, ev in enumerate(hp.last_events)))
 
     # ---- second headline: c64b3 NN-policy playouts (mcts_nn root evaluations, config 3/4 shape) ----
     log("fixed-order block done")

@@ -25,6 +25,14 @@ for G, number in ((1, 12), (1, 1300), (world, 12), (2 * world + 1, 12)):  # repl
     ok &= same and same_f
     if rank == 0:
         print(f"G={G} number={number}: plan {d.shard_plan(G, number, rank, world)} mcts_nn {'ok' if same else 'MISMATCH'}, mcts_fixed {'ok' if same_f else 'MISMATCH'}", flush=True)
+# pipelined root evaluations: three [G,4] exchanges in flight (async_op) before the first is waited for
+origins = eng.init_boards(2 * world + 1, 31, 0)
+want = [d.mcts_nn_sharded(blob, "fp16", origins, 12, 50 + k, 100 * k)["min"].clone() for k in range(3)]
+pend = [d.mcts_nn_sharded(blob, "fp16", origins, 12, 50 + k, 100 * k, async_reduce=True) for k in range(3)]
+same_p = all(torch.equal(d.mcts_nn_finish(r)["min"], w) for r, w in zip(pend, want))
+ok &= same_p
+if rank == 0:
+    print(f"pipelined mcts_nn (3 exchanges in flight) {'ok' if same_p else 'MISMATCH'}", flush=True)
 recs, mv = pkg.selfplay.selfplay_batch(2 * world + 1, 6, None, 2, seed=9)
 single = eng.selfplay_fixed_games(2 * world + 1, 6, 9, times=2, mode=2)
 steps = single["steps"].cpu().numpy()
