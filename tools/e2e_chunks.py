@@ -23,13 +23,13 @@ for k in range(3):
     eng.playout_fixed(n, 2 + k, 0, start=start, out=out)
 e1.record(); torch.cuda.synchronize()
 print(f"device-resident: {e0.elapsed_time(e1) / 3:.2f} ms per step", flush=True)
-for chunks in (2, 3, 4, 6, 8, 12, 16, 24, 32):
-    hp = eng.HostPlayout(n, chunks=chunks)
+for chunks, ramp in [(c, False) for c in (2, 3, 4, 6, 8, 12, 16)] + [(c, True) for c in (5, 7, 9, 11, 15)]:
+    hp = eng.HostPlayout(n, chunks=chunks, ramp=ramp)
     hp(h_start, 3000, 0)
     torch.cuda.synchronize()
     e0.record()
     for k in range(4):
         hp(h_start, 4000 + k, 0)
     e1.record(); torch.cuda.synchronize()
-    print(f"chunks={chunks:3d}: {e0.elapsed_time(e1) / 4:.2f} ms per step", flush=True)
+    print(f"chunks={chunks:3d}{' ramp' if ramp else '     '}: {e0.elapsed_time(e1) / 4:.2f} ms per step", flush=True)
     del hp
