@@ -672,8 +672,8 @@ def main():
                      "executed": executed,
                      "note": "frac = algorithmic 250 thread-instr/move (SURVEY 8d: the reference-shaped attempt cascade) x moves/s vs %d SM x 4 x 32 x "
                              "%.0f MHz (%s clocks); it exceeds 1 because the pair-table kernel does less work per move than that model "
-                             "(`executed`: thread-instr/move and pipe utilisation from the committed ncu capture; the ALU pipe is the binder, "
-                             "shared-memory wavefronts second); HBM sees only %.1f GB/s of %.0f"
+                             "(`executed`: thread-instr/move and pipe utilisation from the committed ncu capture; the ALU pipe and the "
+                             "shared-memory wavefronts, both ~89 %% busy, bind it); HBM sees only %.1f GB/s of %.0f"
                              % (sm_count, peaks["sm_max_mhz"], peak_kind, hbm_bytes / (ms * 1e-3) / 1e9 / world,
                                 peaks["hbm_gbs"])},
     }
