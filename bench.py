@@ -328,15 +328,27 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     moves = torch.zeros(1, dtype=torch.int64, device="cuda")
     l0 = lc()
     e0.record()
+    # Independent evaluations are pipelined twice over: (1) launches alternate between two streams, so the persistent CTAs of
+    # evaluation k+1 take over the SMs that evaluation k's CTAs leave while its last lines are still running (the library is
+    # re-entrant per stream); (2) the [G,4] MIN exchange of evaluation k is only enqueued (dist.allreduce_root_stats async_op),
+    # so a rank does not wait for the slowest rank at every step.  Every launch and exchange completes inside the timed region.
+    cur = torch.cuda.current_stream()
+    lanes = [torch.cuda.Stream(), torch.cuda.Stream()] if not args.nn_one_stream else [cur, cur]
+    for st in lanes:
+        st.wait_stream(cur)
+    part = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in lanes]
     inflight = []
     for k in range(args.steps):
-        # independent evaluations are pipelined: a rank starts evaluation k+1 while the [G,4] MIN exchange of evaluation k
-        # waits for the slowest rank (dist.allreduce_root_stats async_op); every exchange completes inside the timed region
-        r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G, async_reduce=True)
-        moves += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
-        inflight.append(r)
-    for r in inflight:
-        d.mcts_nn_finish(r)
+        with torch.cuda.stream(lanes[k & 1]):
+            r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G, async_reduce=True)
+            part[k & 1] += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
+            inflight.append((k & 1, r))
+    for i, r in inflight:
+        with torch.cuda.stream(lanes[i]):
+            d.mcts_nn_finish(r)
+    for st in lanes:
+        cur.wait_stream(st)
+    moves += part[0] + part[1]
     e1.record()
     barrier()
     launches = lc() - l0
@@ -476,6 +488,7 @@ def main():
     ap.add_argument("--sp-games", type=int, default=256, help="config 4: main games in TOTAL (sharded over the GPUs)")
     ap.add_argument("--sp-steps", type=int, default=8, help="config 4: main moves per main game per step")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-policy block")
+    ap.add_argument("--nn-one-stream", action="store_true", help="nn_policy block: launch the evaluations on one stream (A/B)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall target of the cpu_baseline sample")
     args = ap.parse_args()
