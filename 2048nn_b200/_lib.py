@@ -31,6 +31,7 @@ _SIGS = {
     "b2048_destroy": (C.c_int, [P]),
     "b2048_num_sms": (C.c_int, [P]),
     "b2048_launch_count": (i64, [P]),
+    "b2048_probe_pipe_rate": (C.c_int, [P, C.c_int, u32, P, C.POINTER(u64), P]),
     "b2048_set_playout_variant": (C.c_int, [P, C.c_int]),
     "b2048_set_latency_mode": (C.c_int, [P, C.c_int]),
     "b2048_take_error_flag": (C.c_int, [P, P, C.POINTER(C.c_int)]),

@@ -11,6 +11,7 @@
 #include "engine_kernels.cuh"
 #include "playout_nn.cuh"
 #include "selfplay_kernels.cuh"
+#include "probe.cuh"
 
 using namespace b2048;
 
@@ -140,6 +141,23 @@ extern "C" int b2048_destroy(b2048_ctx *c) {
 
 extern "C" int b2048_num_sms(const b2048_ctx *c) { return c ? c->num_sms : 0; }
 extern "C" int64_t b2048_launch_count(const b2048_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
+
+/* Measurement aid (bench.py roofline.executed.measured_pipe_rates): one launch of the pipe-rate probe, #SMs CTAs x 1024
+ * threads x iters x 64 probe instructions (kind 0: LOP3 = ALU pipe; kind 1: LOP3 + IMAD alternating = issue limit). */
+extern "C" int b2048_probe_pipe_rate(b2048_ctx *c, int kind, uint32_t iters, uint32_t *sink, uint64_t *out_thread_instr,
+                                     void *stream) {
+    if (!c || !sink || !out_thread_instr) return fail_msg("b2048_probe_pipe_rate: NULL argument");
+    if (kind < 0 || kind > 1) return fail_msg("b2048_probe_pipe_rate: kind must be 0 (LOP3) or 1 (LOP3 + IMAD)");
+    DeviceGuard dg(c->device);
+    *out_thread_instr = (uint64_t)c->num_sms * 1024ULL * (uint64_t)iters * (uint64_t)PROBE_UNROLL;
+    if (iters == 0) return 0;
+    if (kind == 0)
+        pipe_probe_kernel<0><<<LC(c, c->num_sms), 1024, 0, (cudaStream_t)stream>>>(iters, 0x9E3779B9u, 0x7F4A7C15u, sink);
+    else
+        pipe_probe_kernel<1><<<LC(c, c->num_sms), 1024, 0, (cudaStream_t)stream>>>(iters, 0x9E3779B9u, 0x7F4A7C15u, sink);
+    CK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int b2048_set_latency_mode(b2048_ctx *c, int mode) {
     if (mode < 0 || mode > 2) return fail_msg("b2048_set_latency_mode: mode must be 0, 1 or 2");

@@ -313,6 +313,27 @@ def num_sms(device=None):
     return int(L.load_library().b2048_num_sms(L.ctx(device)))
 
 
+def pipe_rate(kind, iters=20000, reps=3, device=None):
+    """Measured SM integer pipe rate in thread-instructions per second (b2048_probe_pipe_rate; the denominators of the K2
+    roofline): kind 0 = LOP3 only (ALU pipe), kind 1 = LOP3 + IMAD alternating (the issue limit).  Device timed, best of
+    `reps` after one warm-up launch."""
+    lib, ctx = L.load_library(), L.ctx(device)
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+    sink = torch.zeros(1, dtype=torch.int32, device=dev)
+    n = C.c_uint64(0)
+    best = 0.0
+    with torch.cuda.device(dev):
+        for r in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(lib.b2048_probe_pipe_rate(ctx, int(kind), int(iters), L.ptr(sink), C.byref(n), L.stream_ptr(dev)))
+            e1.record()
+            e1.synchronize()
+            if r:
+                best = max(best, n.value / (e0.elapsed_time(e1) * 1e-3))
+    return best
+
+
 def game_summary(finals, score, moves=None, acc=None, want_maxtile=False):
     """Accumulate the distribution summary of finished games (b2048_game_summary) into acc (int64[20], created
     zeroed when None).  -> (acc, maxtile u8[n] or None)"""

@@ -333,22 +333,24 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     # re-entrant per stream); (2) the [G,4] MIN exchange of evaluation k is only enqueued (dist.allreduce_root_stats async_op),
     # so a rank does not wait for the slowest rank at every step.  Every launch and exchange completes inside the timed region.
     cur = torch.cuda.current_stream()
-    lanes = [torch.cuda.Stream(), torch.cuda.Stream()] if not args.nn_one_stream else [cur, cur]
+    lanes = [torch.cuda.Stream() for _ in range(max(2, args.nn_lanes))] if not args.nn_one_stream else [cur]
     for st in lanes:
         st.wait_stream(cur)
     part = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in lanes]
     inflight = []
     for k in range(args.steps):
-        with torch.cuda.stream(lanes[k & 1]):
+        i = k % len(lanes)
+        with torch.cuda.stream(lanes[i]):
             r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G, async_reduce=True)
-            part[k & 1] += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
-            inflight.append((k & 1, r))
+            part[i] += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
+            inflight.append((i, r))
     for i, r in inflight:
         with torch.cuda.stream(lanes[i]):
             d.mcts_nn_finish(r)
     for st in lanes:
         cur.wait_stream(st)
-    moves += part[0] + part[1]
+    for p_ in part:
+        moves += p_
     e1.record()
     barrier()
     launches = lc() - l0
@@ -489,6 +491,7 @@ def main():
     ap.add_argument("--sp-steps", type=int, default=8, help="config 4: main moves per main game per step")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-policy block")
     ap.add_argument("--nn-one-stream", action="store_true", help="nn_policy block: launch the evaluations on one stream (A/B)")
+    ap.add_argument("--nn-lanes", type=int, default=2, help="nn_policy block: streams the independent evaluations alternate between")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall target of the cpu_baseline sample")
     args = ap.parse_args()
@@ -608,6 +611,8 @@ def main():
 
     # ---- second headline: c64b3 NN-policy playouts (mcts_nn root evaluations, config 3/4 shape) ----
     log("fixed-order block done")
+    # measured denominators of the K2 roofline: what this GPU sustains on LOP3 alone (the ALU pipe) and on LOP3 + IMAD (issue limit)
+    pipe_rates = {"alu_lop3": eng.pipe_rate(0), "issue_lop3_imad": eng.pipe_rate(1)} if rank == 0 else None
     nn = nn_policy_block(pkg, args, rank, world, barrier) if not args.no_nn else None
     log("training block")
     tr = train_step_block(pkg, args, rank, world, barrier) if not args.no_train else None
@@ -667,6 +672,15 @@ def main():
                         "ncu_issue_active_pct": tinfo.get("issue_active_pct"),
                         "ncu_shared_wavefronts_pct_of_peak": tinfo.get("shared_wavefronts_pct_of_peak"),
                         "source": "committed ncu capture (profiles/r02_k2_traffic_16m.json), not measured in this run"}
+            if pipe_rates:
+                # live probes (b2048_probe_pipe_rate, csrc/probe.cuh): full warps of LOP3 / LOP3+IMAD on every SM, device timed
+                executed["measured_pipe_rates"] = {
+                    "alu_pipe_thread_instr_per_s": pipe_rates["alu_lop3"], "issue_thread_instr_per_s": pipe_rates["issue_lop3_imad"],
+                    "alu_formula_at_max_clock": issue_peak / 2, "issue_formula_at_max_clock": issue_peak,
+                    "alu_pipe_frac_of_measured": (per_gpu_moves_per_s * tinfo["alu_pipe_lane_slots_per_move"] / pipe_rates["alu_lop3"]
+                                                  if tinfo.get("alu_pipe_lane_slots_per_move") else None),
+                    "issue_frac_of_measured": per_gpu_moves_per_s * measured_instr / pipe_rates["issue_lop3_imad"],
+                    "note": "probe kernels measured in this run; per-move instruction counts from the committed ncu capture"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

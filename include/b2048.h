@@ -65,6 +65,14 @@ int b2048_num_sms(const b2048_ctx *ctx);
 /* kernels launched through this context since b2048_create (launch accounting of bench.py's gpu_launches) */
 int64_t b2048_launch_count(const b2048_ctx *ctx);
 
+/* Measurement aid for the K2 roofline (SURVEY 8d bounds the fixed-order playout by SM integer issue): one launch of a
+ * pipe-rate probe on `stream`, #SMs CTAs x 1024 threads x iters x 64 probe instructions.  kind 0 = LOP3 only (the ALU pipe,
+ * which ncu shows as K2's first binder), kind 1 = LOP3 and IMAD alternating (ALU + FMA pipes: the issue limit).  `sink` is a
+ * 4-byte device scratch word; *out_thread_instr (host) receives the number of probe thread-instructions of the launch.  The
+ * caller times the launch with events: thread-instructions / second is the measured denominator bench.py reports. */
+int b2048_probe_pipe_rate(b2048_ctx *ctx, int kind, uint32_t iters, uint32_t *sink, uint64_t *out_thread_instr,
+                          void *stream);
+
 /* Fixed-order playout kernel variant: 2 (default) = both slides of a row in one shared-memory word, the four
  * candidate boards from 8 lookups; 1 = legality table first, then one uniform table slide per move; 0 = the
  * L,U,D,R attempt cascade.  All are bit-exact; the switch exists for A/B measurements. */

@@ -78,6 +78,51 @@ def test_boardarray_loop_equals_play_fixed(board, eg):
     assert arr.fast_move_batch([(0, 1, 3, 2)] * 2) is True and arr.boards == before
 
 
+def test_boardarray_policy_rows_vs_oracle(board, orc, eg):
+    """move_batch / fast_move_batch with PER-GAME priority rows (the (N,4) int64 tensor eval_nn.py:41-42 and
+    mcts_nn.py:36-37 pass) against the oracle's step, over whole games: survivors stay in order, the dead are returned in
+    list order with their last boards, scores accumulate from 0; fast_move_batch advances exactly like move_batch while
+    every game moves and returns True, array untouched, at the first step with a death (board.py:279-303)."""
+    import torch
+
+    seed, n = 97531, 300
+    rng = np.random.default_rng(5)
+    starts = eg["pf_start"][:n].astype(np.uint64)  # fresh boards: the first death comes after a few dozen steps
+    arr = board.BoardArray([int(x) for x in starts], seed=seed)
+    fast = board.BoardArray([int(x) for x in starts], seed=seed)
+    fast_live = True
+    ob, osc = starts.copy(), np.zeros(n, np.uint64)
+    sidx, alive = np.zeros(n, np.uint32), np.ones(n, np.uint8)
+    keys = np.array([orc.rng_key(seed, g) for g in range(n)], np.uint64)
+    steps = 0
+    while arr.boards:
+        live = np.nonzero(alive)[0]
+        rows = np.stack([rng.permutation(4) for _ in live]).astype(np.int64)
+        prio = np.zeros((n, 4), np.uint8)
+        prio[live] = rows
+        before_b, before_s = ob.copy(), osc.copy()
+        deaths = orc.policy_step(ob, osc, sidx, keys, prio, alive)
+        died = [g for g in live if not alive[g]]
+        assert deaths == len(died)
+        move_list = torch.from_numpy(rows) if steps % 2 == 0 else [tuple(int(v) for v in r) for r in rows]
+        if fast_live:
+            snapshot = (list(fast.boards), list(fast.scores))
+            hit = fast.fast_move_batch(move_list)
+            assert hit is (deaths > 0)
+            if hit:
+                assert (fast.boards, fast.scores) == snapshot  # untouched
+                fast_live = False
+        ds, db = arr.move_batch(move_list, get_boards=True)
+        assert ds == [int(before_s[g]) for g in died] and db == [int(before_b[g]) for g in died]
+        keep = np.nonzero(alive)[0]
+        assert arr.boards == [int(ob[g]) for g in keep] and arr.scores == [int(osc[g]) for g in keep]
+        if fast_live:
+            assert fast.boards == arr.boards and fast.scores == arr.scores
+        steps += 1
+    assert steps > 50 and not fast_live and len(fast.boards) == n
+    assert arr.move_batch([], get_boards=True) == ([], []) and arr.fast_move_batch([]) is False
+
+
 def test_mcts_fixed_family(mcts, eg):
     number, seed = int(eg["mc_number"]), int(eg["mc_seed"])
     for e, o in enumerate(eg["mc_origins"].tolist()):

@@ -280,3 +280,13 @@ def test_encode_kernel_streams_at_hbm_rate(eng):
     gbs = n * 1032 / (e0.elapsed_time(e1) * 1e-3) / 1e9
     assert gbs > 2000, gbs
     assert float(x.sum().item()) == n * 16.0
+
+
+def test_pipe_rate_probes(eng):
+    # the measured denominators of the K2 roofline (bench.py roofline.executed.measured_pipe_rates): LOP3 alone fills the
+    # ALU pipe (16 lanes per clock and sub-partition), LOP3 + IMAD together fill the issue slots (32 lanes per clock)
+    sms = eng.num_sms()
+    alu, issue = eng.pipe_rate(0, iters=4000), eng.pipe_rate(1, iters=4000)
+    lo, hi = sms * 4 * 16 * 1.0e9, sms * 4 * 16 * 2.2e9  # any SM clock between 1.0 and 2.2 GHz
+    assert lo < alu < hi, alu
+    assert 1.7 * alu < issue < 2.1 * alu, (alu, issue)
