@@ -65,7 +65,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->rowstat, 65536 * sizeof(uint2)));
     CK(cudaMalloc(&c->pair, K3_ROWS * sizeof(uint32_t)));
     c->k2_variant = 2;
-    c->tc_wide = 2;
+    c->tc_wide = 3;
     // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
     // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
     // line queue behind the slots the one-set kernel is the faster one up to ~10,000 lines in flight (profiles/r02_main_single_pct.txt).
@@ -106,6 +106,10 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpecWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpecWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpec3Work, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpec3Work, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
@@ -160,7 +164,7 @@ extern "C" int b2048_probe_pipe_rate(b2048_ctx *c, int kind, uint32_t iters, uin
 }
 
 extern "C" int b2048_set_latency_mode(b2048_ctx *c, int mode) {
-    if (mode < 0 || mode > 2) return fail_msg("b2048_set_latency_mode: mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail_msg("b2048_set_latency_mode: mode must be 0, 1, 2 or 3");
     c->tc_wide.store(mode);
     return 0;
 }
@@ -549,6 +553,18 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
         }
         const int lat = c->tc_wide.load();
         const bool wide = p.single_set && models == 1 && precision == B2048_PREC_FP16_TC && lat >= 1;
+        if (wide && lat >= 3 && total <= (long)c->num_sms * SPEC3_LINES) {
+            // deepest latency regime (config 3: 200 lines on 148 SMs): three-ply speculation, 2 lines x 16 slots per tile
+            grid = grid_for(total, SPEC3_LINES, c->num_sms);
+            if (p.main_mode)
+                tc::tc_persistent_kernel<MainSpec3Work, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<PlaySpec3Work, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            CK(cudaGetLastError());
+            return 0;
+        }
         if (wide && lat >= 2 && total <= (long)c->num_sms * SPEC_LINES) {
             // latency regime (config 3: 200 lines): two-ply speculation, 6 lines x 5 slots per tile, one tile per CTA
             grid = grid_for(total, SPEC_LINES, c->num_sms);

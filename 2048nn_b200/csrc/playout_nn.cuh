@@ -580,9 +580,52 @@ __device__ __forceinline__ void nn_move_spec(const NNPlayParams &p, GameSlot &g,
     moves_done++;
 }
 
+// Three-ply speculation (even fewer lines: at most 2 per SM, e.g. BASELINE config 3 = 200 lines on 148 SMs).  A line owns
+// SPEC3_GROUP = 16 slots of a tile: slot 0 its current board, slots 1..4 the boards after move d (+ the spawn its stream has
+// already fixed), slots 5..15 the first 11 boards -- in (d, e) order -- that follow from a legal second move e.  One forward
+// evaluates all of them, so the line plays up to THREE policy moves per forward; when the pair it plays is not among the 11
+// evaluated ones it plays two.  `pairs` = bit 4d+e set when the board after moves d, e exists.
+constexpr int SPEC3_GROUP = 16, SPEC3_LINES = 2, SPEC3_GRAND = SPEC3_GROUP - 5;
+__device__ __forceinline__ void nn_move_spec3(const NNPlayParams &p, GameSlot &g, const float *logits, const SlotCand *cands,
+                                              int lead, u32 pairs, u32 &moves_done) {
+    const int gmin = cands[lead].gmin;
+    int slot = lead;
+#pragma unroll 1
+    for (int ply = 0; ply < 3; ply++) {
+        if (g.group >= 0 && (int)g.count >= gmin) {
+            nn_finish(p, g);
+            return;
+        }
+        const SlotCand &c = cands[slot];
+        const int b = best_legal(logits + 4 * slot, c.legal);
+        if (b < 0) {
+            nn_finish(p, g);
+            return;
+        }
+        if ((c.legal >> (8 + b)) & 1u) {
+            *p.err_flag = 1;
+            nn_finish(p, g);
+            return;
+        }
+        g.board = c.next[b];
+        g.score += c.score[b];
+        g.count++;
+        moves_done++;
+        if (ply == 0) {
+            slot = lead + 1 + b;  // the board just reached was evaluated by child slot b
+        } else if (ply == 1) {
+            const int idx = 4 * (slot - lead - 1) + b;
+            const int rank = __popc(pairs & ((1u << idx) - 1u));
+            if (!((pairs >> idx) & 1u) || rank >= SPEC3_GRAND) return;  // that grandchild was not evaluated: two plies this time
+            slot = lead + 5 + rank;
+        }
+    }
+}
+
 // MAIN = true: the device-resident main-game mode (slots are fed by the line queue, mg_service), a separate kernel
-// instantiation so that the plain playout kernel carries none of its code.  SPEC = true: two-ply speculation (above).
-template <bool MAIN, bool SPEC = false>
+// instantiation so that the plain playout kernel carries none of its code.  SPEC = 1: two-ply speculation, SPEC = 2:
+// three-ply speculation (above).
+template <bool MAIN, int SPEC = 0>
 struct PlayWorkT {
     typedef NNPlayParams Params;
     struct State {
@@ -593,11 +636,15 @@ struct PlayWorkT {
         // index of the spawn that follows a move from it
         u64 my_board, my_key;
         u32 my_draw;
+        u32 pairs;  // SPEC == 2: which (first move, second move) successors of the line's board exist (nn_move_spec3)
     };
     __device__ static size_t blob_offset(const Params &p) {
         return p.n_models > 1 ? (size_t)(blockIdx.x % (unsigned)p.n_models) * (size_t)p.blob_stride : 0;
     }
-    __device__ static bool is_leader(int lane) { return !SPEC || (lane < SPEC_GROUP * SPEC_LINES && lane % SPEC_GROUP == 0); }
+    __device__ static bool is_leader(int lane) {
+        if (SPEC == 2) return (lane & (SPEC3_GROUP - 1)) == 0;
+        return !SPEC || (lane < SPEC_GROUP * SPEC_LINES && lane % SPEC_GROUP == 0);
+    }
     __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
         st.g.closing = 0;
@@ -607,7 +654,7 @@ struct PlayWorkT {
         st.g.count = 0;
         st.g.group = -1;
         st.moves_done = 0;
-        st.my_board = 0, st.my_key = 0, st.my_draw = 0;
+        st.my_board = 0, st.my_key = 0, st.my_draw = 0, st.pairs = 0;
         // latency mode (few work items): one tile-set per CTA so a step is not interleaved with a second set
         st.queue_empty = (set > 0) && p.single_set;
         if (SPEC && !is_leader((int)(threadIdx.x & 31))) st.queue_empty = true;  // successor slots never take work items
@@ -630,12 +677,44 @@ struct PlayWorkT {
         dbg_base = 0;
         const bool lead = is_leader(lane);
         if (!first && st.g.live) {
-            if (SPEC) nn_move_spec(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.moves_done);
+            if (SPEC == 2) nn_move_spec3(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.pairs, st.moves_done);
+            else if (SPEC) nn_move_spec(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.moves_done);
             else nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
         }
         if (MAIN) mg_service(p, st.g, lead, st.queue_empty, lane, false);
         else if (lead && !st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
-        if (SPEC) {
+        if (SPEC == 2) {
+            // lane 16 l + 4 d + e of line l computes the board after moves d, e (with the two spawns the line's stream has
+            // already fixed); the legal ones are packed, in (d, e) order, into the line's 11 grandchild slots
+            const int sub = lane & (SPEC3_GROUP - 1), src = lane & SPEC3_GROUP;
+            const u64 lb = __shfl_sync(0xffffffffu, st.g.board, src), lk = __shfl_sync(0xffffffffu, st.g.key, src);
+            const u32 lc = __shfl_sync(0xffffffffu, st.g.count, src);
+            const int ll = __shfl_sync(0xffffffffu, st.g.live, src);
+            u64 child = 0, grand = 0;
+            if (ll) {
+                u32 sc, four;
+                const u64 f = move_exact(lb, sub >> 2, p.tb, sc);
+                if (f != lb && countzero(f) != 0) {
+                    child = spawn_tile(f, rng_draw(lk, B2048_INIT_DRAWS + p.spawn0 + lc), four);  // == SlotCand.next[d] of the leader
+                    const u64 f2 = move_exact(child, sub & 3, p.tb, sc);
+                    if (f2 != child && countzero(f2) != 0)
+                        grand = spawn_tile(f2, rng_draw(lk, B2048_INIT_DRAWS + p.spawn0 + lc + 1u), four);
+                }
+            }
+            const u32 pairs = (__ballot_sync(0xffffffffu, grand != 0) >> src) & 0xFFFFu;
+            // slot `sub` of the line: 0 = the line's board, 1..4 = child d = sub - 1 (held by lane 4 d), 5..15 = the
+            // (sub - 5)-th existing grandchild
+            const u32 nth = sub >= 5 ? __fns(pairs, 0, sub - 4) : 0xFFFFFFFFu;
+            const u64 cb = __shfl_sync(0xffffffffu, child, src + ((sub >= 1 && sub <= 4) ? 4 * (sub - 1) : 0));
+            const u64 gb = __shfl_sync(0xffffffffu, grand, src + (nth < 16u ? (int)nth : 0));
+            u64 mine = 0;
+            u32 draw = lc;
+            if (sub == 0) mine = ll ? lb : 0ULL;
+            else if (sub <= 4) mine = cb, draw = lc + 1u;
+            else if (nth < 16u) mine = gb, draw = lc + 2u;
+            st.my_board = mine, st.my_key = lk, st.my_draw = draw, st.pairs = pairs;
+            s_boards[lane] = mine;
+        } else if (SPEC) {
             // the line's leader hands its board / stream / move count to its four successor slots
             const int sub = lane % SPEC_GROUP, src = (lane < SPEC_GROUP * SPEC_LINES) ? lane - sub : 0;
             const u64 lb = __shfl_sync(0xffffffffu, st.g.board, src), lk = __shfl_sync(0xffffffffu, st.g.key, src);
@@ -670,7 +749,9 @@ struct PlayWorkT {
 };
 typedef PlayWorkT<false> PlayWork;
 typedef PlayWorkT<true> MainWork;
-typedef PlayWorkT<false, true> PlaySpecWork;
-typedef PlayWorkT<true, true> MainSpecWork;
+typedef PlayWorkT<false, 1> PlaySpecWork;
+typedef PlayWorkT<true, 1> MainSpecWork;
+typedef PlayWorkT<false, 2> PlaySpec3Work;
+typedef PlayWorkT<true, 2> MainSpec3Work;
 
 }  // namespace b2048

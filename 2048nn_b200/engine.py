@@ -304,7 +304,8 @@ def set_playout_variant(variant, device=None):
 
 def set_latency_mode(mode, device=None):
     """Small tensor-core launches (b2048_set_latency_mode): 0 = no latency variant, 1 = 16-warp one-set kernel,
-    2 (default) = + two-ply speculation for launches with few lines.  Results are identical in every mode."""
+    2 = + two-ply speculation for launches with few lines (<= 6 per SM), 3 (default) = + three-ply speculation for
+    launches with at most 2 lines per SM.  Results are identical in every mode."""
     L.check(L.load_library().b2048_set_latency_mode(L.ctx(device), int(mode)))
 
 

@@ -748,9 +748,10 @@ def main():
             "gpu_launches": g1["launches"],
             "config": {"workload": "1 fresh main game x %d main moves per step, each main move = 4 root moves x %d policy lines "
                                    "with the min-move early stop; %s" % (args.game_steps, args.nn_lines, nn["weights"]),
-                       "parallelism": "replicas only: one main game is 200 lines; with two-ply speculation (each line's board and its "
-                                      "four successors in one forward) they occupy 34 of 148 SMs and the call is bound by the longest "
-                                      "line's dependent forwards (%d GPU(s) run the same game)" % world}}
+                       "parallelism": "replicas only: one main game is 200 lines; with three-ply speculation (each line's board, its "
+                                      "four successors and up to 11 of their successors in one forward: up to three policy moves per "
+                                      "forward) they occupy 100 of 148 SMs and the call is bound by the longest line's dependent "
+                                      "forwards (%d GPU(s) run the same game)" % world}}
         line["selfplay256"] = {
             "metric": "BASELINE config 4: %d main games in TOTAL x mcts_nn(number=%d), device-resident, sharded by game" % (args.sp_games, args.nn_lines),
             "value": spb["moves"] / (spb["ms"] * 1e-3), "unit": UNIT, "scaling": "strong",

@@ -82,10 +82,13 @@ int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
  *   mode 1  launches with at most one 32-board tile per SM (forward of <= 32 x #SMs boards, root evaluations / main games
  *           with <= 32 x #SMs lines; main games up to 2.5x that) run one tile-set per CTA with all 16 worker warps on its
  *           epilogue;
- *   mode 2  (default) additionally, playouts with at most 6 x #SMs lines in flight (BASELINE config 3: 200 lines) run with
- *           two-ply speculation: a line's current board and its four successors are evaluated in one forward, so every
- *           forward advances the line by two policy moves (half the dependent forwards per mcts_nn call);
- *   mode 0  both off (A/B measurements). */
+ *   mode 2  additionally, playouts with at most 6 x #SMs lines in flight run with two-ply speculation: a line's current
+ *           board and its four successors are evaluated in one forward, so every forward advances the line by two policy
+ *           moves (half the dependent forwards per mcts_nn call);
+ *   mode 3  (default) additionally, playouts with at most 2 x #SMs lines in flight (BASELINE config 3: 200 lines) run with
+ *           three-ply speculation: the line's board, its four successors and up to 11 of their successors in one forward,
+ *           up to three policy moves per forward;
+ *   mode 0  all off (A/B measurements). */
 int b2048_set_latency_mode(b2048_ctx *ctx, int mode);
 
 /* Device error flag: set when a spawn met countzero == 0 (the reference raises ValueError from

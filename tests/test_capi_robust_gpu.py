@@ -130,15 +130,16 @@ def test_context_of_another_gpu_from_one_process(pkg):
 
 def test_latency_modes_give_identical_results(pkg, net, ng):
     # mode 0: two tile-sets / 8-warp groups only; 1: 16-warp one-set kernel for small launches; 2: + two-ply speculation
-    # (a line's board and its four successors in one forward).  Same boards evaluated, same logits, same moves: every
-    # result must be bit-identical.  Sizes chosen so that mode 2 really speculates (<= 6 x #SMs lines in flight).
+    # (a line's board and its four successors in one forward); 3: + three-ply speculation (up to 11 second successors as
+    # well).  Same boards evaluated, same logits, same moves: every result must be bit-identical.  Sizes chosen so that
+    # modes 2 and 3 really speculate (<= 6 x #SMs resp. <= 2 x #SMs lines in flight).
     eng = pkg.engine
     blob = net.blob("fp16")
     origins = eng.init_boards(3, 9, 0)
     boards = torch.from_numpy(ng["lg_boards"][:1000].view(np.int64).copy()).cuda()
     ref = None
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             eng.set_latency_mode(mode)
             r = eng.mcts_nn_lines(blob, "fp16", origins, 20, 77, 5, per_line=False)
             g = eng.playout_nn(blob, "fp16", 100, 78, 0)
@@ -158,4 +159,4 @@ def test_latency_modes_give_identical_results(pkg, net, ng):
                     assert torch.equal(a, b), (mode, k)
         assert pkg._lib.take_error_flag() == 0
     finally:
-        eng.set_latency_mode(2)
+        eng.set_latency_mode(3)

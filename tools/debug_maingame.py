@@ -13,7 +13,7 @@ blob = m.blob("fp16")
 eng.selfplay_nn_games(blob, "fp16", 1, 4, 5, max_steps=1)
 torch.cuda.synchronize()
 ref = {}
-for wide in (2, 1, 0):
+for wide in (3, 2, 1, 0):
     eng.set_latency_mode(wide)
     for G, number, steps in ((1, 50, 16), (4, 50, 8), (8, 50, 4)):
         t0 = time.perf_counter()
@@ -34,7 +34,7 @@ for wide in (2, 1, 0):
         lp = m.forward_boards(b)
     e1.record(); torch.cuda.synchronize()
     print(f"latency_mode={wide} forward 1024 boards: {e0.elapsed_time(e1)/20*1e3:.1f} us, max|dlogp| vs reference {np.abs(lp.cpu().numpy() - ng['lg_shipped'][:1024]).max():.4f}", flush=True)
-eng.set_latency_mode(2)
+eng.set_latency_mode(3)
 for G, number, steps in ((64, 50, 4), (256, 50, 2), (256, 50, 8), (32, 50, 8)):
     t0 = time.perf_counter()
     r = eng.selfplay_nn_games(blob, "fp16", G, number, 5, max_steps=steps)
