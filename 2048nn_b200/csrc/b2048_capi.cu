@@ -66,6 +66,7 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaMalloc(&c->pair, K3_ROWS * sizeof(uint32_t)));
     c->k2_variant = 2;
     c->tc_wide = 3;
+    if (const char *e = getenv("B2048_LATENCY_MODE")) c->tc_wide = atoi(e) < 0 ? 0 : (atoi(e) > 3 ? 3 : atoi(e));  // A/B runs only
     // Measured on B200 (tools/debug_maingame.py): two tile-sets per CTA reach 1.9e8 policy moves/s when all 9,472 slots
     // are busy but take ~50 us per step; one tile-set (16-warp latency variant) takes ~31 us with 4,736 slots.  With a
     // line queue behind the slots the one-set kernel is the faster one up to ~10,000 lines in flight (profiles/r02_main_single_pct.txt).
@@ -108,6 +109,10 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpecWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpec3Work, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayAdaptWork, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayAdaptWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpec3Work, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
@@ -586,10 +591,21 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
                 tc::tc_persistent_kernel<MainWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                     p, (const uint8_t *)p.blob, nullptr, -1, 0);
         } else if (wide) {
-            tc::tc_persistent_kernel<PlayWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
-                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            // latency modes >= 2, whole-game launches (eval_nn / population evaluation: long games of very different
+            // lengths): the tail of the launch (queue empty, few lines left per tile) speculates (PlayAdaptWork).  Root
+            // evaluations keep the plain kernel: their early stop makes the tail short, and the adaptive policy's longer
+            // engine phase measured 1.5 % slower there.
+            if (lat >= 2 && !p.root_mode)
+                tc::tc_persistent_kernel<PlayAdaptWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<PlayWork, false, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
         } else if (precision == B2048_PREC_BF16_TC)
             tc::tc_persistent_kernel<PlayWork, false, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        else if (lat >= 2 && !p.root_mode)
+            tc::tc_persistent_kernel<PlayAdaptWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
         else
             tc::tc_persistent_kernel<PlayWork, false><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(

@@ -624,26 +624,32 @@ __device__ __forceinline__ void nn_move_spec3(const NNPlayParams &p, GameSlot &g
 
 // MAIN = true: the device-resident main-game mode (slots are fed by the line queue, mg_service), a separate kernel
 // instantiation so that the plain playout kernel carries none of its code.  SPEC = 1: two-ply speculation, SPEC = 2:
-// three-ply speculation (above).
+// three-ply speculation (above), both for launches that are small from the start.
+// SPEC = 3 (ADAPTIVE, not with MAIN): a tile-set starts with one line per slot; once the launch's work queue is empty and
+// at most 6 (2) of its 32 lines are still running, the survivors are moved to the leader slots of the two-ply (three-ply)
+// layout and the free slots evaluate their successors: the tail of a launch -- a few long lines holding an SM each --
+// then runs at two to three policy moves per forward.  The boards evaluated are the boards the plain kernel evaluates,
+// so every result is identical.
 template <bool MAIN, int SPEC = 0>
 struct PlayWorkT {
+    static_assert(!(MAIN && SPEC == 3), "main-game launches have no tail: their slots are fed by the line queue");
     typedef NNPlayParams Params;
     struct State {
         GameSlot g;
         u32 moves_done;
         bool queue_empty;
-        // SPEC: the board this slot evaluates (a line's current board or one of its four successors), its stream and the
-        // index of the spawn that follows a move from it
-        u64 my_board, my_key;
-        u32 my_draw;
-        u32 pairs;  // SPEC == 2: which (first move, second move) successors of the line's board exist (nn_move_spec3)
+        // speculation layouts: a successor slot is never live; it keeps the board it evaluates, the line's stream and the
+        // index of the spawn that follows a move from that board in its own g.board / g.key / g.count
+        u32 pairs;  // three-ply layout: which (first move, second move) successors of the line's board exist (nn_move_spec3)
+        int mode;   // layout of this tile-set: 0 = one line per slot, 1 = two-ply groups, 2 = three-ply groups
     };
     __device__ static size_t blob_offset(const Params &p) {
         return p.n_models > 1 ? (size_t)(blockIdx.x % (unsigned)p.n_models) * (size_t)p.blob_stride : 0;
     }
-    __device__ static bool is_leader(int lane) {
-        if (SPEC == 2) return (lane & (SPEC3_GROUP - 1)) == 0;
-        return !SPEC || (lane < SPEC_GROUP * SPEC_LINES && lane % SPEC_GROUP == 0);
+    __device__ static int mode_of(const State &st) { return SPEC == 3 ? st.mode : SPEC; }
+    __device__ static bool is_leader(int mode, int lane) {
+        if (mode == 2) return (lane & (SPEC3_GROUP - 1)) == 0;
+        return mode == 0 || (lane < SPEC_GROUP * SPEC_LINES && lane % SPEC_GROUP == 0);
     }
     __device__ static void init(State &st, const Params &p, int set) {
         st.g.live = 0;
@@ -653,37 +659,65 @@ struct PlayWorkT {
         st.g.key = 0;
         st.g.count = 0;
         st.g.group = -1;
+        st.g.score = 0;
         st.moves_done = 0;
-        st.my_board = 0, st.my_key = 0, st.my_draw = 0, st.pairs = 0;
+        st.pairs = 0;
+        st.mode = SPEC == 3 ? 0 : SPEC;
         // latency mode (few work items): one tile-set per CTA so a step is not interleaved with a second set
         st.queue_empty = (set > 0) && p.single_set;
-        if (SPEC && !is_leader((int)(threadIdx.x & 31))) st.queue_empty = true;  // successor slots never take work items
+        if (!is_leader(st.mode, (int)(threadIdx.x & 31))) st.queue_empty = true;  // successor slots never take work items
     }
     __device__ static void prefetch(const Params &p, State &st, uint8_t *scratch, int lane) {
         SlotCand *c = reinterpret_cast<SlotCand *>(scratch) + lane;
-        if (SPEC) {
-            if (!st.my_board) return;
-            const bool lead = is_leader(lane);
-            fill_cand(p, c, st.my_board, st.my_key, st.my_draw,
-                      (lead && st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff);
-            return;
-        }
-        if (!st.g.live) return;
+        const int mode = mode_of(st);
+        const bool lead = is_leader(mode, lane);
+        if (lead ? !st.g.live : !st.g.board) return;  // (successor slots exist in the speculation layouts only)
         fill_cand(p, c, st.g.board, st.g.key, st.g.count,
-                  (st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff);
+                  (lead && st.g.group >= 0) ? *((volatile int *)(p.group_min + st.g.group)) : 0x7fffffff);
+    }
+    // ADAPTIVE: move the k-th live line of the set to lane k * stride (the leader slots of the next layout)
+    __device__ static void compact(State &st, unsigned live, int stride, int lane) {
+        const int k = lane / stride;
+        const bool target = (lane % stride == 0) && k < __popc(live);
+        const int src = target ? (int)__fns(live, 0, k + 1) : lane;
+        GameSlot &g = st.g;
+        g.board = __shfl_sync(0xffffffffu, g.board, src);
+        g.key = __shfl_sync(0xffffffffu, g.key, src);
+        g.score = __shfl_sync(0xffffffffu, g.score, src);
+        g.count = __shfl_sync(0xffffffffu, g.count, src);
+        g.slot = __shfl_sync(0xffffffffu, g.slot, src);
+        g.group = __shfl_sync(0xffffffffu, g.group, src);
+        g.live = target ? 1 : 0;
+        g.closing = 0;
+        st.queue_empty = true;
     }
     __device__ static int step(const Params &p, State &st, bool first, const float *logits, unsigned long long *s_boards,
                                int lane, long &dbg_base, uint8_t *scratch) {
         dbg_base = 0;
-        const bool lead = is_leader(lane);
+        int mode = mode_of(st);
+        const bool lead = is_leader(mode, lane);
         if (!first && st.g.live) {
-            if (SPEC == 2) nn_move_spec3(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.pairs, st.moves_done);
-            else if (SPEC) nn_move_spec(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.moves_done);
+            if (mode == 2) nn_move_spec3(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.pairs, st.moves_done);
+            else if (mode == 1) nn_move_spec(p, st.g, logits, reinterpret_cast<const SlotCand *>(scratch), lane, st.moves_done);
             else nn_move_cand(p, st.g, logits + 4 * lane, reinterpret_cast<const SlotCand *>(scratch)[lane], st.moves_done);
         }
         if (MAIN) mg_service(p, st.g, lead, st.queue_empty, lane, false);
         else if (lead && !st.g.live && !st.queue_empty) st.queue_empty = !nn_fetch(p, st.g);
-        if (SPEC == 2) {
+        if (SPEC == 3 && mode < 2) {
+            // the queue is empty (every free slot has seen it) and few lines are left: regroup them so that the free slots
+            // evaluate their successors
+            const unsigned live = __ballot_sync(0xffffffffu, st.g.live);
+            const unsigned open = __ballot_sync(0xffffffffu, !st.g.live && !st.queue_empty);
+            const int n = __popc(live);
+            if (!open && n > 0 && n < 32) {
+                const int want = n <= SPEC3_LINES ? 2 : (n <= SPEC_LINES ? 1 : 0);
+                if (want > mode) {
+                    compact(st, live, want == 2 ? SPEC3_GROUP : SPEC_GROUP, lane);
+                    st.mode = mode = want;
+                }
+            }
+        }
+        if (mode == 2) {
             // lane 16 l + 4 d + e of line l computes the board after moves d, e (with the two spawns the line's stream has
             // already fixed); the legal ones are packed, in (d, e) order, into the line's 11 grandchild slots
             const int sub = lane & (SPEC3_GROUP - 1), src = lane & SPEC3_GROUP;
@@ -712,16 +746,18 @@ struct PlayWorkT {
             if (sub == 0) mine = ll ? lb : 0ULL;
             else if (sub <= 4) mine = cb, draw = lc + 1u;
             else if (nth < 16u) mine = gb, draw = lc + 2u;
-            st.my_board = mine, st.my_key = lk, st.my_draw = draw, st.pairs = pairs;
+            st.pairs = pairs;
+            if (sub) st.g.board = mine, st.g.key = lk, st.g.count = draw;
             s_boards[lane] = mine;
-        } else if (SPEC) {
+        } else if (mode == 1) {
             // the line's leader hands its board / stream / move count to its four successor slots
+            const bool lead1 = is_leader(1, lane);
             const int sub = lane % SPEC_GROUP, src = (lane < SPEC_GROUP * SPEC_LINES) ? lane - sub : 0;
             const u64 lb = __shfl_sync(0xffffffffu, st.g.board, src), lk = __shfl_sync(0xffffffffu, st.g.key, src);
             const u32 lc = __shfl_sync(0xffffffffu, st.g.count, src);
             const int ll = __shfl_sync(0xffffffffu, st.g.live, src);
             u64 mine = 0;
-            if (lead) {
+            if (lead1) {
                 mine = st.g.live ? st.g.board : 0ULL;
             } else if (lane < SPEC_GROUP * SPEC_LINES && ll) {
                 u32 sc;
@@ -731,7 +767,7 @@ struct PlayWorkT {
                     mine = spawn_tile(f, rng_draw(lk, B2048_INIT_DRAWS + p.spawn0 + lc), four);  // == SlotCand.next[sub - 1] of the leader
                 }
             }
-            st.my_board = mine, st.my_key = lk, st.my_draw = lead ? lc : lc + 1u;
+            if (!lead1) st.g.board = mine, st.g.key = lk, st.g.count = lc + 1u;
             s_boards[lane] = mine;
         } else {
             s_boards[lane] = st.g.live ? st.g.board : 0ULL;
@@ -753,5 +789,6 @@ typedef PlayWorkT<false, 1> PlaySpecWork;
 typedef PlayWorkT<true, 1> MainSpecWork;
 typedef PlayWorkT<false, 2> PlaySpec3Work;
 typedef PlayWorkT<true, 2> MainSpec3Work;
+typedef PlayWorkT<false, 3> PlayAdaptWork;
 
 }  // namespace b2048

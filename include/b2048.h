@@ -84,7 +84,8 @@ int b2048_set_playout_variant(b2048_ctx *ctx, int variant);
  *           epilogue;
  *   mode 2  additionally, playouts with at most 6 x #SMs lines in flight run with two-ply speculation: a line's current
  *           board and its four successors are evaluated in one forward, so every forward advances the line by two policy
- *           moves (half the dependent forwards per mcts_nn call);
+ *           moves (half the dependent forwards per mcts_nn call); and in the TAIL of any larger playout launch (work queue
+ *           empty, at most 6 / 2 lines left in a 32-slot tile) the survivors are regrouped into the two- / three-ply layout;
  *   mode 3  (default) additionally, playouts with at most 2 x #SMs lines in flight (BASELINE config 3: 200 lines) run with
  *           three-ply speculation: the line's board, its four successors and up to 11 of their successors in one forward,
  *           up to three policy moves per forward;

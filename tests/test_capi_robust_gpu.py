@@ -145,11 +145,16 @@ def test_latency_modes_give_identical_results(pkg, net, ng):
             g = eng.playout_nn(blob, "fp16", 100, 78, 0)
             grp = eng.playout_nn(blob, "fp16", 120, 79, 0, group_size=30)
             sp = eng.selfplay_nn_games(blob, "fp16", 2, 10, 80, max_steps=2048)
+            # whole-game launches too big to speculate from the start: modes >= 2 regroup the survivors of every tile in the
+            # tail of the launch (one-set kernel at 3,000 games, two tile-sets at 12,000)
+            big1 = eng.playout_nn(blob, "fp16", 3000, 81, 0)
+            big2 = eng.playout_nn(blob, "fp16", 12000, 82, 0, group_size=40)
             fw = net.forward_boards(boards, precision="fp16")
             torch.cuda.synchronize()
             n0, n1 = int(sp["steps"][0]), int(sp["steps"][1])
             got = [r["minmov"], g["final"], g["score"], g["moves"], grp["group_min"], sp["final"], sp["score"], sp["steps"],
-                   sp["boards"][0, :n0], sp["boards"][1, :n1], sp["results"][0, :n0], fw]
+                   sp["boards"][0, :n0], sp["boards"][1, :n1], sp["results"][0, :n0], fw,
+                   big1["final"], big1["score"], big1["moves"], big2["group_min"]]
             assert int(g["total_moves"].item()) == int(g["moves"].sum().item())
             assert n0 > 20 and n1 > 20 and int(sp["status"].sum()) == 0
             if ref is None:
