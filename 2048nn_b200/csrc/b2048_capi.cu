@@ -114,6 +114,11 @@ extern "C" int b2048_create(int device, b2048_ctx **out) {
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayAdaptWork, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpecWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpecWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlaySpec3Work, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpec3Work, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<PlayAdaptWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<MainSpec3Work, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             tc::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::tc_persistent_kernel<tc::FwdWork, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -532,8 +537,30 @@ static int launch_nn(b2048_ctx *c, int precision, NNPlayParams &p, cudaStream_t 
     if (precision == B2048_PREC_FP16X2_TC) {
         if (models > 1) return fail_msg("b2048 NN playout: the precise tensor-core mode plays one model per launch");
         p.single_set = 1;
-        const int grid = grid_for(total, tc::TILE_BOARDS, c->num_sms);
-        if (p.main_mode)
+        int grid = grid_for(total, tc::TILE_BOARDS, c->num_sms);
+        const int lat = c->tc_wide.load();
+        // the latency regimes of the throughput mode (below): three- / two-ply speculation for small launches, adaptive
+        // tail speculation for whole-game launches
+        if (lat >= 3 && total <= (long)c->num_sms * SPEC3_LINES) {
+            grid = grid_for(total, SPEC3_LINES, c->num_sms);
+            if (p.main_mode)
+                tc::tc_persistent_kernel<MainSpec3Work, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<PlaySpec3Work, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        } else if (lat >= 2 && total <= (long)c->num_sms * SPEC_LINES) {
+            grid = grid_for(total, SPEC_LINES, c->num_sms);
+            if (p.main_mode)
+                tc::tc_persistent_kernel<MainSpecWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+            else
+                tc::tc_persistent_kernel<PlaySpecWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                    p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        } else if (lat >= 2 && !p.main_mode && !p.root_mode)
+            tc::tc_persistent_kernel<PlayAdaptWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
+                p, (const uint8_t *)p.blob, nullptr, -1, 0);
+        else if (p.main_mode)
             tc::tc_persistent_kernel<MainWork, false, false, true, true><<<LC(c, grid), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(
                 p, (const uint8_t *)p.blob, nullptr, -1, 0);
         else

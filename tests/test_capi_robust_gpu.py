@@ -147,6 +147,12 @@ def test_latency_modes_give_identical_results(pkg, net, ng):
             sp = eng.selfplay_nn_games(blob, "fp16", 2, 10, 80, max_steps=2048)
             # whole-game launches too big to speculate from the start: modes >= 2 regroup the survivors of every tile in the
             # tail of the launch (one-set kernel at 3,000 games, two tile-sets at 12,000)
+            # the precise tensor-core mode goes through the same latency regimes
+            blob2 = net.blob("fp16x2")
+            r2 = eng.mcts_nn_lines(blob2, "fp16x2", origins, 20, 77, 5, per_line=False)
+            g2 = eng.playout_nn(blob2, "fp16x2", 100, 78, 0)
+            sp2 = eng.selfplay_nn_games(blob2, "fp16x2", 2, 10, 80, max_steps=40)
+            big3 = eng.playout_nn(blob2, "fp16x2", 1500, 83, 0)
             big1 = eng.playout_nn(blob, "fp16", 3000, 81, 0)
             big2 = eng.playout_nn(blob, "fp16", 12000, 82, 0, group_size=40)
             fw = net.forward_boards(boards, precision="fp16")
@@ -154,7 +160,8 @@ def test_latency_modes_give_identical_results(pkg, net, ng):
             n0, n1 = int(sp["steps"][0]), int(sp["steps"][1])
             got = [r["minmov"], g["final"], g["score"], g["moves"], grp["group_min"], sp["final"], sp["score"], sp["steps"],
                    sp["boards"][0, :n0], sp["boards"][1, :n1], sp["results"][0, :n0], fw,
-                   big1["final"], big1["score"], big1["moves"], big2["group_min"]]
+                   big1["final"], big1["score"], big1["moves"], big2["group_min"],
+                   r2["minmov"], g2["final"], g2["moves"], sp2["boards"], sp2["results"], sp2["steps"], big3["final"], big3["moves"]]
             assert int(g["total_moves"].item()) == int(g["moves"].sum().item())
             assert n0 > 20 and n1 > 20 and int(sp["status"].sum()) == 0
             if ref is None:
