@@ -415,10 +415,19 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     rp = eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 401, 0)
     q1.record()
     torch.cuda.synchronize()
+    # config 3 in the precise mode: one main game x 16 mcts_nn(number=50) main moves, device-resident
+    eng.selfplay_nn_games(blob2, "fp16x2", 1, number, 500, max_steps=4)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    rg = eng.selfplay_nn_games(blob2, "fp16x2", 1, number, 501, max_steps=16)
+    g1.record()
+    torch.cuda.synchronize()
     precise = {"forward_boards_per_s_per_gpu": 3 * nb / (p0.elapsed_time(p1) * 1e-3),
                "nn_policy_moves_per_s_per_gpu": float(rp["total_moves"].item()) / (q0.elapsed_time(q1) * 1e-3),
+               "mcts_nn_game_ms_per_main_move": g0.elapsed_time(g1) / max(1, int(rg["steps"].sum().item())),
                "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC): max |dlogp| < 1e-2 on all 150,371 fixture boards "
-                       "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block, one GPU"}
+                       "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block / mcts_nn_game (one main game, number=%d), one GPU" % number}
     import copy
     torch_base = torch_forward_baselines(pkg, copy.deepcopy(m), fb) if rank == 0 else None
     # config 3 (one main game, mcts_nn number=50 per main move) and config 4 (256 main games in total, sharded)
