@@ -69,6 +69,10 @@ constexpr int TMEM_COLS = 512;
 // second 84 KB image, so the mode exists for the one-set (WIDE) kernel only: the lo image lives where set 1's image would.
 // Weight stream: chunk (l, dy) is followed by its lo chunk for l in [1, 3] -> 30 chunks per forward.
 constexpr int SPLIT_FIRST = 1, SPLIT_LAST = 3;
+// The correction passes of a split layer (x_lo * w_hi, x_hi * w_lo) run over the first SPLIT_NK K steps = 32 input channels
+// only: the host orders the channels by their share of the rounding error (convnet.split_channel_order), and the first 32
+// carry nearly all of it (tools/precision_study3.py: max |dlogp| 0.0058 on the 150k-board fixture, 0.0052 with all 64).
+constexpr int SPLIT_NK = 2;
 constexpr int N_CHUNKS_PRECISE = N_CHUNKS + 3 * (SPLIT_LAST - SPLIT_FIRST + 1);
 __host__ __device__ constexpr bool layer_is_split(int l) { return l >= SPLIT_FIRST && l <= SPLIT_LAST; }
 
@@ -515,14 +519,14 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                     if (PRECISE && layer_is_split(l)) {
                         // precise mode (one set): + x_lo * w_hi on the same chunk, then the layer's lo chunk: + x_hi * w_lo
                         issue_half((sm_base + SM_ACT + ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                                   (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
                         umma_commit_elect(bars.empty0 + 8 * slot);
                         cons++;
                         slot = cons % RING;
                         mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
                         tc_fence_after();
                         issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                                   (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
                     }
                     umma_commit_elect(bars.empty0 + 8 * slot);  // this half's "slot reusable"
                     cons++;
@@ -580,14 +584,14 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                     if (PRECISE && layer_is_split(l)) {
                         // precise mode, one set: + x_lo * w_hi on the same chunk, then the layer's lo chunk: + x_hi * w_lo
                         issue_half((sm_base + SM_ACT + ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                                   (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
                         umma_commit_elect(bars.empty0 + 8 * slot);
                         cons++;
                         const uint32_t slot2 = cons % RING;
                         mbar_wait(bars.full0 + 8 * slot2, (cons / RING) & 1);
                         tc_fence_after();
                         issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot2 * CHUNK_BYTES) >> 4,
-                                   (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16, false);
+                                   (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
                         umma_commit_elect(bars.empty0 + 8 * slot2);
                         cons++;
                         have_chunk = false;  // both chunks of this (layer, dy) are released
