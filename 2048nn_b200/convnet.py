@@ -136,8 +136,8 @@ def pack_tc(folded, dtype="fp16", precise=False, calib_boards=None):
     """16-bit tensor-core blob (dtype "fp16" or "bf16"): 21 chunks (layer l, ky) of 192 rows [kx=2 | kx=1 | kx=0] x 64 co, each row
     64 ci fp16 (K-major, pre-swizzled); L0 rows are [W_hi(16 ci) | W_lo(16 ci) | 0]; then the fp32 tail
     bias[7][64], w7[4][64], b7[4], fcw[4][64], fcb[4].
-    precise=True (B2048_PREC_FP16X2_TC, fp16 only): every chunk of layers 1..3 is followed by its lo chunk
-    fp16(W - fp16(W)) -> 30 chunks; the channels are reordered (split_channel_order on `calib_boards`) so that the kernel's
+    precise=True (B2048_PREC_FP16X2_TC, fp16 only): layers 1..3 carry two lo chunks fp16(W - fp16(W)) of their first 32 input
+    channels ([ky 0 | ky 1] after the second chunk, [ky 2 | 0] after the third) -> 27 chunks; the channels are reordered (split_channel_order on `calib_boards`) so that the kernel's
     correction passes over the first SPLIT_CHANNELS input channels cover the ones that matter."""
     if precise and dtype != "fp16":
         raise ValueError("the precise tensor-core mode is fp16 hi+lo")
@@ -164,11 +164,17 @@ def pack_tc(folded, dtype="fp16", precise=False, calib_boards=None):
                 raise ValueError("folded weights overflow " + dtype)
             chunks.append(_swizzle_rows(bits).reshape(-1))
             if precise and l in SPLIT_LAYERS:
-                lo_rows = np.zeros((TC_CHUNK_ROWS, 64), np.float64)
+                # lo weights fp16(W - fp16(W)) of the first SPLIT_CHANNELS input channels; a 64-column row holds the halves of
+                # two taps side by side: chunk X = [ky 0 | ky 1] follows the layer's second chunk, Y = [ky 2 | 0] its third
+                if ky != 1:
+                    lo_rows = np.zeros((TC_CHUNK_ROWS, 64), np.float64)
+                col = SPLIT_CHANNELS if ky == 1 else 0
                 for blk, kx in enumerate((2, 1, 0)):
-                    lo_rows[blk * 64:(blk + 1) * 64, :] = w[:, :, ky, kx] - vals[blk * 64:(blk + 1) * 64, :].astype(np.float64)
-                lo_bits, _ = _to16(lo_rows.astype(np.float32), dtype)
-                chunks.append(_swizzle_rows(lo_bits).reshape(-1))
+                    lo_rows[blk * 64:(blk + 1) * 64, col:col + SPLIT_CHANNELS] = (
+                        w[:, :SPLIT_CHANNELS, ky, kx] - vals[blk * 64:(blk + 1) * 64, :SPLIT_CHANNELS].astype(np.float64))
+                if ky >= 1:
+                    lo_bits, _ = _to16(lo_rows.astype(np.float32), dtype)
+                    chunks.append(_swizzle_rows(lo_bits).reshape(-1))
     wbytes = np.concatenate(chunks).view(np.uint8)
     tail = np.concatenate([np.stack(folded["conv_b"]).reshape(-1), folded["head_w"].reshape(-1), folded["head_b"],
                            folded["fc_w"].reshape(-1), folded["fc_b"]]).astype(np.float32)

@@ -73,7 +73,10 @@ constexpr int SPLIT_FIRST = 1, SPLIT_LAST = 3;
 // only: the host orders the channels by their share of the rounding error (convnet.split_channel_order), and the first 32
 // carry nearly all of it (tools/precision_study3.py: max |dlogp| 0.0058 on the 150k-board fixture, 0.0052 with all 64).
 constexpr int SPLIT_NK = 2;
-constexpr int N_CHUNKS_PRECISE = N_CHUNKS + 3 * (SPLIT_LAST - SPLIT_FIRST + 1);
+// lo chunks of a split layer: X = [w_lo(dy=-1) ci 0..31 | w_lo(dy=0) ci 0..31] after the layer's second chunk, Y = [w_lo(dy=+1)
+// ci 0..31 | 0] after its third: a 128-byte row holds the 32-channel halves of two taps side by side, so the correction
+// needs two extra chunks per layer, not three, and no chunk is consumed faster than the ring refills
+constexpr int N_CHUNKS_PRECISE = N_CHUNKS + 2 * (SPLIT_LAST - SPLIT_FIRST + 1);
 __host__ __device__ constexpr bool layer_is_split(int l) { return l >= SPLIT_FIRST && l <= SPLIT_LAST; }
 
 // blob: [21 (precise: 30) chunks fp16, pre-swizzled] [fp32 tail: bias 7x64 | w7 4x64 | b7 4 | fcw 4x64 | fcb 4]
@@ -517,19 +520,28 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                     issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
                                (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16);
                     if (PRECISE && layer_is_split(l)) {
-                        // precise mode (one set): + x_lo * w_hi on the same chunk, then the layer's lo chunk: + x_hi * w_lo
+                        // precise mode (one set): + x_lo * w_hi on the same chunk (first SPLIT_NK K steps)
                         issue_half((sm_base + SM_ACT + ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
-                                   (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
-                        umma_commit_elect(bars.empty0 + 8 * slot);
-                        cons++;
-                        slot = cons % RING;
-                        mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
-                        tc_fence_after();
-                        issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
                                    (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
                     }
                     umma_commit_elect(bars.empty0 + 8 * slot);  // this half's "slot reusable"
                     cons++;
+                    if (PRECISE && layer_is_split(l) && dyi >= 1) {
+                        // + x_hi * w_lo from the layer's lo chunks: X = [dy 0 | dy 1] after the second chunk, Y = [dy 2 | -]
+                        // after the third (K steps [0, SPLIT_NK) and [SPLIT_NK, 2 SPLIT_NK) of the chunk's rows)
+                        slot = cons % RING;
+                        mbar_wait(bars.full0 + 8 * slot, (cons / RING) & 1);
+                        tc_fence_after();
+                        const uint32_t in_hi = (sm_base + SM_ACT + set * ACT_BYTES) >> 4, wlo = (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4;
+                        if (dyi == 1) {
+                            issue_half(in_hi, wlo, (uint32_t)(set * 256), desc_hi, 0, SPLIT_NK, half, bf16, false);
+                            issue_half(in_hi, wlo + 2 * SPLIT_NK, (uint32_t)(set * 256), desc_hi, 1, SPLIT_NK, half, bf16, false);
+                        } else {
+                            issue_half(in_hi, wlo, (uint32_t)(set * 256), desc_hi, 2, SPLIT_NK, half, bf16, false);
+                        }
+                        umma_commit_elect(bars.empty0 + 8 * slot);
+                        cons++;
+                    }
                     if (dyi == 2) {
                         umma_commit_elect(bars.acc0 + 8 * set);  // this half of the set's accumulators
                         if (half == 0) TC_TRACE(trace_iter, (l * 2 + set) * 8 + 1);
@@ -538,6 +550,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                 }
             }
 #else
+            static_assert(!PRECISE, "the dy-interleaved order (trace builds) does not know the precise mode's lo-chunk layout");
             for (int dyi = 0; dyi < 3; dyi++) {
                 const uint32_t slot = cons % RING;
                 bool have_chunk = false;
@@ -646,7 +659,8 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
                 if (!LAST) {
                     pw[jj] = pack_relu_x2<BF16>(a0, a1);
                     if (KEEP_RES) res[xi][c * 4 + jj] = pw[jj];
-                    if (WRITE_LO) {  // what the rounding to fp16 dropped, itself rounded to fp16 (no ReLU: it has a sign)
+                    if (WRITE_LO && c < 2 * SPLIT_NK) {  // what the rounding to fp16 dropped, itself rounded to fp16 (no ReLU:
+                                                          // it has a sign); only the channels the correction passes read
                         const float2 h = unpack_x2<BF16>(pw[jj]);
                         const float l0 = fmaxf(a0, 0.f) - h.x, l1 = fmaxf(a1, 0.f) - h.y;
                         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[jj]) : "f"(l1), "f"(l0));
@@ -654,7 +668,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t row0, uint32_t row1, uin
                 }
             }
             if (!LAST) sts_u4((xi ? row1 : row0) + (((uint32_t)c << 4) ^ sw16), pw[0], pw[1], pw[2], pw[3]);
-            if (!LAST && WRITE_LO)
+            if (!LAST && WRITE_LO && c < 2 * SPLIT_NK)
                 sts_u4((xi ? row1 : row0) + (uint32_t)ACT_BYTES + (((uint32_t)c << 4) ^ sw16), pl[0], pl[1], pl[2], pl[3]);
             if (DBG && dbg0) {
 #pragma unroll

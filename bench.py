@@ -407,14 +407,23 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     p1.record()
     torch.cuda.synchronize()
     blob2 = m.blob("fp16x2")
-    org1 = origins[:args.nn_origins].contiguous()
+    org1 = origins[rank * args.nn_origins:(rank + 1) * args.nn_origins].contiguous()  # this rank's own origins
     eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 400, 0)
     torch.cuda.synchronize()
+    barrier()
     q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     q0.record()
-    rp = eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 401, 0)
+    rp = eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 401, rank * args.nn_origins)
     q1.record()
     torch.cuda.synchronize()
+    # whole job in the precise mode: every rank evaluates its own 256 origins (weak scaling, no collective on this path);
+    # moves summed over ranks / slowest rank's device time
+    pj = torch.tensor([q0.elapsed_time(q1), float(rp["total_moves"].item())], dtype=torch.float64, device="cuda")
+    pj_ms = pj[:1].clone()
+    if world > 1:
+        torch.distributed.all_reduce(pj_ms, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(pj, op=torch.distributed.ReduceOp.SUM)
+    precise_job = float(pj[1].item()) / (float(pj_ms[0].item()) * 1e-3)
     # config 3 in the precise mode: one main game x 16 mcts_nn(number=50) main moves, device-resident
     eng.selfplay_nn_games(blob2, "fp16x2", 1, number, 500, max_steps=4)
     torch.cuda.synchronize()
@@ -425,6 +434,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     torch.cuda.synchronize()
     precise = {"forward_boards_per_s_per_gpu": 3 * nb / (p0.elapsed_time(p1) * 1e-3),
                "nn_policy_moves_per_s_per_gpu": float(rp["total_moves"].item()) / (q0.elapsed_time(q1) * 1e-3),
+               "nn_policy_moves_per_s_all_gpus": precise_job,
                "mcts_nn_game_ms_per_main_move": g0.elapsed_time(g1) / max(1, int(rg["steps"].sum().item())),
                "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC: fp16 hi+lo operands on L1-L3, 32 most important input channels): max |dlogp| 0.0066 < 1e-2 on all 150,371 fixture boards "
                        "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block / mcts_nn_game (one main game, number=%d), one GPU" % number}
