@@ -321,40 +321,50 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     G, number = args.nn_origins * world, args.nn_lines
     origins = eng.init_boards(G, 4242, 0)  # synthetic fresh start boards, same on every rank
     log("nn_policy: root evaluations")
-    for w in range(max(3, args.warmup)):
-        d.mcts_nn_sharded(blob, "fp16", origins, number, 100 + w, 0)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    moves = torch.zeros(1, dtype=torch.int64, device="cuda")
-    l0 = lc()
-    e0.record()
+
+    def timed_evaluations(blob, prec, steps, warm, seed0):
+        """`steps` pipelined root evaluations of all G origins (sharded by dist.shard_plan), device timed; -> (ms, moves of this
+        rank as a device tensor, launches)"""
+        cur = torch.cuda.current_stream()
+        lanes = [torch.cuda.Stream() for _ in range(max(2, args.nn_lanes))] if not args.nn_one_stream else [cur]
+        for w in range(warm):  # warm-up on the lanes themselves (the first launch on a fresh stream was seen to cost ~0.1 s once)
+            lanes[w % len(lanes)].wait_stream(cur)
+            with torch.cuda.stream(lanes[w % len(lanes)]):
+                d.mcts_nn_sharded(blob, prec, origins, number, seed0 + w, 0)
+        for st in lanes:
+            cur.wait_stream(st)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        moves = torch.zeros(1, dtype=torch.int64, device="cuda")
+        l0 = lc()
+        e0.record()
+        for st in lanes:
+            st.wait_stream(cur)
+        part = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in lanes]
+        inflight = []
+        for k in range(steps):
+            i = k % len(lanes)
+            with torch.cuda.stream(lanes[i]):
+                r = d.mcts_nn_sharded(blob, prec, origins, number, seed0 + 100 + k, k * G, async_reduce=True)
+                part[i] += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
+                inflight.append((i, r))
+        for i, r in inflight:
+            with torch.cuda.stream(lanes[i]):
+                d.mcts_nn_finish(r)
+        for st in lanes:
+            cur.wait_stream(st)
+        for p_ in part:
+            moves += p_
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), moves, lc() - l0
+
     # Independent evaluations are pipelined twice over: (1) launches alternate between two streams, so the persistent CTAs of
     # evaluation k+1 take over the SMs that evaluation k's CTAs leave while its last lines are still running (the library is
     # re-entrant per stream); (2) the [G,4] MIN exchange of evaluation k is only enqueued (dist.allreduce_root_stats async_op),
     # so a rank does not wait for the slowest rank at every step.  Every launch and exchange completes inside the timed region.
-    cur = torch.cuda.current_stream()
-    lanes = [torch.cuda.Stream() for _ in range(max(2, args.nn_lanes))] if not args.nn_one_stream else [cur]
-    for st in lanes:
-        st.wait_stream(cur)
-    part = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in lanes]
-    inflight = []
-    for k in range(args.steps):
-        i = k % len(lanes)
-        with torch.cuda.stream(lanes[i]):
-            r = d.mcts_nn_sharded(blob, "fp16", origins, number, 200 + k, k * G, async_reduce=True)
-            part[i] += r["total_moves"]  # this rank's lines; summed over ranks once, after the timed region
-            inflight.append((i, r))
-    for i, r in inflight:
-        with torch.cuda.stream(lanes[i]):
-            d.mcts_nn_finish(r)
-    for st in lanes:
-        cur.wait_stream(st)
-    for p_ in part:
-        moves += p_
-    e1.record()
-    barrier()
-    launches = lc() - l0
-    ms = e0.elapsed_time(e1)
+    ms, moves, launches = timed_evaluations(blob, "fp16", args.steps, max(3, args.warmup), 100)
     # end to end through the reference-facing call shape: host origins in, host [G,4] results out
     h_orig = origins.cpu().pin_memory()
     h_res = torch.empty((G, 4), dtype=torch.int64).pin_memory()
@@ -416,14 +426,14 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     rp = eng.mcts_nn_lines(blob2, "fp16x2", org1, number, 401, rank * args.nn_origins)
     q1.record()
     torch.cuda.synchronize()
-    # whole job in the precise mode: every rank evaluates its own 256 origins (weak scaling, no collective on this path);
-    # moves summed over ranks / slowest rank's device time
-    pj = torch.tensor([q0.elapsed_time(q1), float(rp["total_moves"].item())], dtype=torch.float64, device="cuda")
-    pj_ms = pj[:1].clone()
+    # whole job in the precise mode: the nn_policy loop above (same origins, sharding, exchange and pipelining) with the
+    # precise weight image, 3 evaluations; moves summed over ranks / slowest rank's device time
+    pj_ms, pj_moves, _ = timed_evaluations(blob2, "fp16x2", 3, 2, 600)
+    d.sum_over_ranks(pj_moves)
+    pj_t = torch.tensor([pj_ms], dtype=torch.float64, device="cuda")
     if world > 1:
-        torch.distributed.all_reduce(pj_ms, op=torch.distributed.ReduceOp.MAX)
-        torch.distributed.all_reduce(pj, op=torch.distributed.ReduceOp.SUM)
-    precise_job = float(pj[1].item()) / (float(pj_ms[0].item()) * 1e-3)
+        torch.distributed.all_reduce(pj_t, op=torch.distributed.ReduceOp.MAX)
+    precise_job = float(pj_moves.item()) / (float(pj_t.item()) * 1e-3)
     # config 3 in the precise mode: one main game x 16 mcts_nn(number=50) main moves, device-resident
     eng.selfplay_nn_games(blob2, "fp16x2", 1, number, 500, max_steps=4)
     torch.cuda.synchronize()
@@ -434,7 +444,7 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     torch.cuda.synchronize()
     precise = {"forward_boards_per_s_per_gpu": 3 * nb / (p0.elapsed_time(p1) * 1e-3),
                "nn_policy_moves_per_s_per_gpu": float(rp["total_moves"].item()) / (q0.elapsed_time(q1) * 1e-3),
-               "nn_policy_moves_per_s_all_gpus": precise_job,
+               "nn_policy_moves_per_s_all_gpus": precise_job,  # the nn_policy loop (3 pipelined evaluations) in the precise mode
                "mcts_nn_game_ms_per_main_move": g0.elapsed_time(g1) / max(1, int(rg["steps"].sum().item())),
                "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC: fp16 hi+lo operands on L1-L3, 32 most important input channels): max |dlogp| 0.0066 < 1e-2 on all 150,371 fixture boards "
                        "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block / mcts_nn_game (one main game, number=%d), one GPU" % number}
