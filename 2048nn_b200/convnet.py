@@ -94,8 +94,9 @@ def split_channel_order(folded, calib_boards):
     the first SPLIT_CHANNELS input channels only, so the channels whose rounding errors matter most -- largest
     E[x_c^2] * sum(w[:, c]^2) on the calibration boards -- must come first.  Returns (stream order, mid order): the residual
     stream (outputs of layers 0, 2, 4, 6 = inputs of layers 1, 3, 5 and of the head) shares one order, chosen for layers 1 and 3
-    together; the output of layer 1 (input of layer 2) has its own.  tools/precision_study3.py: max |dlogp| 0.0058 on the
-    150k-board fixture against 0.0052 with all 64 channels, at half the correction work."""
+    together; the output of layer 1 (input of layer 2) has its own.  tools/precision_study3.py: max |dlogp| 0.0067 on the
+    150k-board fixture against 0.0052 with all 64 channels, at half the correction work (0.0078 in the shipped configuration,
+    which also drops layer 3's activation correction)."""
     import torch.nn.functional as F
 
     x = torch.from_numpy(onehot_np(calib_boards))

@@ -73,6 +73,10 @@ constexpr int SPLIT_FIRST = 1, SPLIT_LAST = 3;
 // only: the host orders the channels by their share of the rounding error (convnet.split_channel_order), and the first 32
 // carry nearly all of it (tools/precision_study3.py: max |dlogp| 0.0058 on the 150k-board fixture, 0.0052 with all 64).
 constexpr int SPLIT_NK = 2;
+// The activation correction (x_lo * w_hi) runs on layers SPLIT_FIRST..SPLIT_A_LAST, the weight correction (x_hi * w_lo) on
+// SPLIT_FIRST..SPLIT_LAST: layer 3's activation correction buys little (tools/precision_study3.py: max |dlogp| 0.0078 without it,
+// 0.0067 with it) and costs half a layer pass plus the lo stores of layer 2's epilogue.
+constexpr int SPLIT_A_LAST = 2;
 // lo chunks of a split layer: X = [w_lo(dy=-1) ci 0..31 | w_lo(dy=0) ci 0..31] after the layer's second chunk, Y = [w_lo(dy=+1)
 // ci 0..31 | 0] after its third: a 128-byte row holds the 32-channel halves of two taps side by side, so the correction
 // needs two extra chunks per layer, not three, and no chunk is consumed faster than the ring refills
@@ -519,7 +523,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                     // whole warp, uniform operands, one elected lane issues; tmem_base is 0 (all 512 columns owned)
                     issue_half((sm_base + SM_ACT + set * ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
                                (uint32_t)(set * 256), desc_hi, dyi, nk, half, bf16);
-                    if (PRECISE && layer_is_split(l)) {
+                    if (PRECISE && layer_is_split(l) && l <= SPLIT_A_LAST) {
                         // precise mode (one set): + x_lo * w_hi on the same chunk (first SPLIT_NK K steps)
                         issue_half((sm_base + SM_ACT + ACT_BYTES) >> 4, (sm_base + SM_RING + slot * CHUNK_BYTES) >> 4,
                                    (uint32_t)(set * 256), desc_hi, dyi, SPLIT_NK, half, bf16, false);
@@ -822,7 +826,7 @@ __device__ __forceinline__ void worker_loop(uint8_t *sm, uint32_t tmem_base, con
                     epilogue_layer<false, true, false, DBG, BF16, NX, PRECISE>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (PRECISE && l == 1)
                     epilogue_layer<false, false, false, DBG, BF16, NX, true>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
-                else if (PRECISE && l == 2)
+                else if (PRECISE && l == 2 && SPLIT_A_LAST >= 3)
                     epilogue_layer<true, true, false, DBG, BF16, NX, true>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);
                 else if (l & 1)
                     epilogue_layer<false, false, false, DBG, BF16, NX>(r0a, r1a, sw16, ba, ta, acc0, res, head_acc, dbg0);

@@ -8,8 +8,8 @@ and returns `(N,4)` log-probabilities computed by the CUDA kernels (b2048_convne
 
 precision: "fp32" = exact mode (CUDA-core FMA, |dlogp| ~1e-5 vs PyTorch);
            "fp16" = tcgen05 tensor-core mode (fp16 operands, fp32 accumulation);
-           "fp16x2" = precise tensor-core mode (layers L1..L3 with fp16 hi+lo weights and activations on their 32 most
-                    important input channels: every board within 1e-2 of the fp32 reference, ~0.6x the throughput of "fp16");
+           "fp16x2" = precise tensor-core mode (fp16 hi+lo weights on layers L1..L3 and activations on L1..L2, on their 32 most
+                    important input channels: every board within 1e-2 of the fp32 reference, ~0.65x the throughput of "fp16");
            "bf16" = the same kernels with bf16 operands (fails the 99.9 % argmax bar on the shipped
                     weights; kept so the choice of fp16 is a measurement, not an assumption).
 Training (autograd through forward) is outside this path and raises.

@@ -427,8 +427,8 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     q1.record()
     torch.cuda.synchronize()
     # whole job in the precise mode: the nn_policy loop above (same origins, sharding, exchange and pipelining) with the
-    # precise weight image, 3 evaluations; moves summed over ranks / slowest rank's device time
-    pj_ms, pj_moves, _ = timed_evaluations(blob2, "fp16x2", 3, 2, 600)
+    # precise weight image, `steps` evaluations; moves summed over ranks / slowest rank's device time
+    pj_ms, pj_moves, _ = timed_evaluations(blob2, "fp16x2", args.steps, 2, 600)
     d.sum_over_ranks(pj_moves)
     pj_t = torch.tensor([pj_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -444,9 +444,9 @@ def nn_policy_block(pkg, args, rank, world, barrier):
     torch.cuda.synchronize()
     precise = {"forward_boards_per_s_per_gpu": 3 * nb / (p0.elapsed_time(p1) * 1e-3),
                "nn_policy_moves_per_s_per_gpu": float(rp["total_moves"].item()) / (q0.elapsed_time(q1) * 1e-3),
-               "nn_policy_moves_per_s_all_gpus": precise_job,  # the nn_policy loop (3 pipelined evaluations) in the precise mode
+               "nn_policy_moves_per_s_all_gpus": precise_job,  # the nn_policy loop (`steps` pipelined evaluations) in the precise mode
                "mcts_nn_game_ms_per_main_move": g0.elapsed_time(g1) / max(1, int(rg["steps"].sum().item())),
-               "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC: fp16 hi+lo operands on L1-L3, 32 most important input channels): max |dlogp| 0.0066 < 1e-2 on all 150,371 fixture boards "
+               "note": "precision=\"fp16x2\" (B2048_PREC_FP16X2_TC: fp16 hi+lo weights on L1-L3 and activations on L1-L2, 32 most important input channels): max |dlogp| 0.0077 < 1e-2 on all 150,371 fixture boards "
                        "(tests/test_network_gpu.py); same workloads as forward_only / one root evaluation of this block / mcts_nn_game (one main game, number=%d), one GPU" % number}
     import copy
     torch_base = torch_forward_baselines(pkg, copy.deepcopy(m), fb) if rank == 0 else None

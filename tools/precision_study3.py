@@ -80,29 +80,6 @@ def emulate(fd, x, split_layers, nch):
     return F.log_softmax(z, 1)
 
 
-def report(name, lp, ref):
-    d = (lp - ref).abs().max(1).values
-    agree = (lp.argmax(1) == ref.argmax(1)).float().mean().item()
-    print(f"  {name:60s} max={d.max():.5f} p99.99={d.quantile(0.9999):.5f} >1e-2: {(d >= 1e-2).sum().item():4d} "
-          f">5e-3: {(d >= 5e-3).sum().item():5d} argmax={100 * agree:.4f}%", flush=True)
-
-
-cal = calibration_boards()
-stream, mid = cn.split_channel_order(folded, cal)
-perm = cn.permute_channels(folded, stream, mid)
-x = torch.from_numpy(cn.onehot_np(fx["boards"][:N]))
-ref = torch.from_numpy(fx["lg_shipped"][:N])
-with torch.no_grad():
-    a, b = forward_fp32(folded, x[:4000]), forward_fp32(perm, x[:4000])
-    print("permuted network == network (fp32, 4000 boards): max |d| %.2e; vs the reference's log-probs %.2e" % ((a - b).abs().max(), (a - ref[:4000]).abs().max()))
-    print("stream order (first 32):", stream[:32].tolist())
-    report("fp16, no correction passes (throughput mode)", emulate(perm, x, (), 0), ref)
-    report("L1-3 hi+lo, all 64 channels (round-2 first version, 13 passes)", emulate(perm, x, (1, 2, 3), 64), ref)
-    report("L1-3 hi+lo, first 32 channels of the calibrated order (10 passes)", emulate(perm, x, (1, 2, 3), 32), ref)
-    report("L1-3 hi+lo, first 16 channels (8.5 passes)", emulate(perm, x, (1, 2, 3), 16), ref)
-    report("L1-3 hi+lo, first 32 channels, NO reordering", emulate(folded, x, (1, 2, 3), 32), ref)
-
-
 def emulate2(fd, x, w_layers, a_layers, nch):
     """as emulate(), with separate layer sets for the weight (hi*lo) and activation (lo*hi) correction passes"""
     w = [torch.from_numpy(np.asarray(a, np.float32)) for a in fd["conv_w"]]
@@ -130,8 +107,32 @@ def emulate2(fd, x, w_layers, a_layers, nch):
     return F.log_softmax(z, 1)
 
 
+def report(name, lp, ref):
+    d = (lp - ref).abs().max(1).values
+    agree = (lp.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"  {name:60s} max={d.max():.5f} p99.99={d.quantile(0.9999):.5f} >1e-2: {(d >= 1e-2).sum().item():4d} "
+          f">5e-3: {(d >= 5e-3).sum().item():5d} argmax={100 * agree:.4f}%", flush=True)
+
+
+cal = calibration_boards()
+stream, mid = cn.split_channel_order(folded, cal)
+perm = cn.permute_channels(folded, stream, mid)
+x = torch.from_numpy(cn.onehot_np(fx["boards"][:N]))
+ref = torch.from_numpy(fx["lg_shipped"][:N])
+with torch.no_grad():
+    a, b = forward_fp32(folded, x[:4000]), forward_fp32(perm, x[:4000])
+    print("permuted network == network (fp32, 4000 boards): max |d| %.2e; vs the reference's log-probs %.2e" % ((a - b).abs().max(), (a - ref[:4000]).abs().max()))
+    print("stream order (first 32):", stream[:32].tolist())
+    report("fp16, no correction passes (throughput mode)", emulate(perm, x, (), 0), ref)
+    report("L1-3 hi+lo, all 64 channels (round-2 first version, 13 passes)", emulate(perm, x, (1, 2, 3), 64), ref)
+    report("L1-3 hi+lo, first 32 channels of the calibrated order (10 passes)", emulate(perm, x, (1, 2, 3), 32), ref)
+    report("THE KERNEL: weights L1-3, activations L1-2, first 32 channels (9.5 passes)", emulate2(perm, x, (1, 2, 3), (1, 2), 32), ref)
+    report("L1-3 hi+lo, first 16 channels (8.5 passes)", emulate(perm, x, (1, 2, 3), 16), ref)
+    report("L1-3 hi+lo, first 32 channels, NO reordering", emulate(folded, x, (1, 2, 3), 32), ref)
+
+
 if os.environ.get("B2048_STUDY_MORE"):
     with torch.no_grad():
-        report("W L1-3 + A L1-2, first 32 channels (9.5 passes)", emulate2(perm, x, (1, 2, 3), (1, 2), 32), ref)
+        report("W L1-2 + A L1-3, first 32 channels (9.5 passes)", emulate2(perm, x, (1, 2), (1, 2, 3), 32), ref)
         report("W L1-2 + A L1-2, first 32 channels (9 passes)", emulate2(perm, x, (1, 2), (1, 2), 32), ref)
         report("W L1-3 + A L1-3, first 48 channels (11.5 passes)", emulate2(perm, x, (1, 2, 3), (1, 2, 3), 48), ref)
