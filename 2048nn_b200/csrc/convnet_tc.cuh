@@ -63,15 +63,15 @@ constexpr int NUM_THREADS = NUM_WARPS * 32;       // 640
 constexpr int WORKER_REGS = 104, CONTROL_REGS = B2048_CONTROL_REGS;  // setmaxnreg pool = launch allocation 640 x 96 = 61,440 >= 16*32*104 + 4*32*56
 constexpr int TMEM_COLS = 512;
 
-// Precise mode (B2048_PREC_FP16X2_TC): the three most error-sensitive layers L1..L3 take BOTH operands as fp16 hi + lo
-// pairs (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate: three MMA passes instead of one), which brings every board of
-// the 150k fixture inside the north-star's 1e-2 (profiles/r02_precision_study.txt).  The lo activation image needs a
+// Precise mode (B2048_PREC_FP16X2_TC): the three most error-sensitive layers L1..L3 take their operands as fp16 hi + lo
+// pairs (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate: the main pass plus two correction passes), which brings every
+// board of the 150k fixture inside the north-star's 1e-2 (profiles/r02_precision_study.txt).  The lo activation image needs a
 // second 84 KB image, so the mode exists for the one-set (WIDE) kernel only: the lo image lives where set 1's image would.
-// Weight stream: chunk (l, dy) is followed by its lo chunk for l in [1, 3] -> 30 chunks per forward.
+// Weight stream: two lo chunks per split layer (below) -> 27 chunks per forward.
 constexpr int SPLIT_FIRST = 1, SPLIT_LAST = 3;
 // The correction passes of a split layer (x_lo * w_hi, x_hi * w_lo) run over the first SPLIT_NK K steps = 32 input channels
 // only: the host orders the channels by their share of the rounding error (convnet.split_channel_order), and the first 32
-// carry nearly all of it (tools/precision_study3.py: max |dlogp| 0.0058 on the 150k-board fixture, 0.0052 with all 64).
+// carry nearly all of it (tools/precision_study3.py: max |dlogp| 0.0067 on the 150k-board fixture, 0.0052 with all 64).
 constexpr int SPLIT_NK = 2;
 // The activation correction (x_lo * w_hi) runs on layers SPLIT_FIRST..SPLIT_A_LAST, the weight correction (x_hi * w_lo) on
 // SPLIT_FIRST..SPLIT_LAST: layer 3's activation correction buys little (tools/precision_study3.py: max |dlogp| 0.0078 without it,
@@ -83,7 +83,7 @@ constexpr int SPLIT_A_LAST = 2;
 constexpr int N_CHUNKS_PRECISE = N_CHUNKS + 2 * (SPLIT_LAST - SPLIT_FIRST + 1);
 __host__ __device__ constexpr bool layer_is_split(int l) { return l >= SPLIT_FIRST && l <= SPLIT_LAST; }
 
-// blob: [21 (precise: 30) chunks fp16, pre-swizzled] [fp32 tail: bias 7x64 | w7 4x64 | b7 4 | fcw 4x64 | fcb 4]
+// blob: [21 (precise: 27) chunks fp16, pre-swizzled] [fp32 tail: bias 7x64 | w7 4x64 | b7 4 | fcw 4x64 | fcb 4]
 constexpr int BLOB_W_BYTES = N_CHUNKS * CHUNK_BYTES;
 constexpr int BLOB_W_BYTES_PRECISE = N_CHUNKS_PRECISE * CHUNK_BYTES;
 constexpr int TAIL_BIAS = 0, TAIL_W7 = 7 * 64, TAIL_B7 = TAIL_W7 + 256, TAIL_FCW = TAIL_B7 + 4,

@@ -194,9 +194,10 @@ int b2048_mcts_fixed(b2048_ctx *ctx, const uint64_t *origins, int64_t G, int num
 #define B2048_PREC_FP32 0
 #define B2048_PREC_FP16_TC 1
 #define B2048_PREC_BF16_TC 2 /* same kernels with bf16 operands: fails the parity bar on the shipped weights, for comparison */
-#define B2048_PREC_FP16X2_TC 3 /* precise tensor-core mode: layers L1..L3 take weights AND activations as fp16 hi+lo pairs
-                                 (three MMA passes), every board of the 150k reference fixture within 1e-2; one tile-set
-                                 per CTA; its own (larger) weight blob */
+#define B2048_PREC_FP16X2_TC 3 /* precise tensor-core mode: layers L1..L3 take their weights, L1..L2 their activations as fp16
+                                 hi+lo pairs on the 32 input channels that carry the rounding error (the blob's channels are
+                                 ordered for it, 2048nn_b200/convnet.py): every board of the 150k reference fixture within
+                                 1e-2 (max 0.0077); one tile-set per CTA; its own (larger) weight blob */
 
 /* size in bytes of the weight blob for a precision (-1: unsupported) */
 int64_t b2048_convnet_blob_bytes(int precision);
