@@ -554,7 +554,7 @@ __device__ __forceinline__ void mma_loop(uint8_t *sm, int half, bool bf16, int n
                 }
             }
 #else
-            static_assert(!PRECISE, "the dy-interleaved order (trace builds) does not know the precise mode's lo-chunk layout");
+            if (PRECISE) __trap();  // the dy-interleaved order (A/B trace builds only) does not know the precise mode's lo-chunk layout
             for (int dyi = 0; dyi < 3; dyi++) {
                 const uint32_t slot = cons % RING;
                 bool have_chunk = false;

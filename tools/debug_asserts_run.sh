@@ -14,7 +14,7 @@ m = pkg.network.ConvNet(64, 3, precision="fp16")
 m.load_state_dict({k[len("sd_random/"):]: torch.from_numpy(np.array(ng[k])) for k in ng.files if k.startswith("sd_random/")})
 m.cuda().eval()
 b = torch.from_numpy(ng["lg_boards"].view(np.int64).copy()).cuda()
-for mode in (0, 1, 2):
+for mode in (0, 1, 2, 3):
     eng.set_latency_mode(mode)
     for prec in ("fp16", "fp16x2"):
         blob = m.blob(prec)
