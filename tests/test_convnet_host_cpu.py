@@ -1,0 +1,89 @@
+"""CPU: host side of the c64b3 weight images (2048nn_b200/convnet.py): BatchNorm folding against the oracle network, the one-hot
+encoder, the channel reordering of the precise tensor-core image (the function must not change) and the blob sizes the C
+library expects."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_dict_from_golden
+
+
+@pytest.fixture(scope="module")
+def cn(pkg):
+    import importlib
+
+    return importlib.import_module("2048nn_b200.convnet")
+
+
+def forward_folded(fd, x):
+    """fp32 forward of a folded network (numpy arrays of convnet.fold_state_dict) with plain torch ops"""
+    import torch.nn.functional as F
+
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float32))  # noqa: E731
+    w, b = [t(a) for a in fd["conv_w"]], [t(a).view(1, -1, 1, 1) for a in fd["conv_b"]]
+    x = F.relu(F.conv2d(x, w[0], padding=1) + b[0])
+    for blk in range(3):
+        h = F.relu(F.conv2d(x, w[1 + 2 * blk], padding=1) + b[1 + 2 * blk])
+        x = F.relu(F.conv2d(h, w[2 + 2 * blk], padding=1) + b[2 + 2 * blk] + x)
+    x = F.relu(F.conv2d(x, t(fd["head_w"]).view(4, 64, 1, 1)) + t(fd["head_b"]).view(1, -1, 1, 1))
+    return F.log_softmax(F.linear(x.reshape(-1, 64), t(fd["fc_w"]), t(fd["fc_b"])), 1)
+
+
+def test_onehot_matches_the_oracle_encoder(cn, orc, ng):
+    boards = ng["lg_boards"][:500]
+    assert torch.equal(torch.from_numpy(cn.onehot_np(boards)), orc.onehot(boards))
+
+
+@pytest.mark.parametrize("tag", ["shipped", "random"])
+def test_folded_network_equals_reference_logits(cn, ng, tag):
+    sd = state_dict_from_golden(ng, tag)
+    fd = cn.fold_state_dict(sd)
+    n = 1500
+    with torch.no_grad():
+        lp = forward_folded(fd, torch.from_numpy(cn.onehot_np(ng["lg_boards"][:n])))
+    assert np.abs(lp.numpy() - ng[f"lg_{tag}"][:n]).max() < 1e-4
+
+
+def test_channel_reordering_keeps_the_function(cn, ng):
+    fd = cn.fold_state_dict(state_dict_from_golden(ng, "shipped"))
+    cal = ng["lg_boards"][2000:3024]
+    stream, mid = cn.split_channel_order(fd, cal)
+    assert sorted(stream.tolist()) == list(range(64)) and sorted(mid.tolist()) == list(range(64))
+    perm = cn.permute_channels(fd, stream, mid)
+    x = torch.from_numpy(cn.onehot_np(ng["lg_boards"][:1000]))
+    with torch.no_grad():
+        a, b = forward_folded(fd, x), forward_folded(perm, x)
+    assert (a - b).abs().max().item() < 2e-5  # same terms, another summation order
+    # the channels the reference never activates on these boards are ranked last on the residual stream
+    with torch.no_grad():
+        import torch.nn.functional as F
+
+        x0 = F.relu(F.conv2d(x, torch.from_numpy(np.asarray(fd["conv_w"][0], np.float32)), padding=1)
+                    + torch.from_numpy(np.asarray(fd["conv_b"][0], np.float32)).view(1, -1, 1, 1))
+    dead0 = set(np.nonzero(x0.amax((0, 2, 3)).numpy() == 0)[0].tolist())
+    assert len(dead0) >= 20 and not (dead0 & set(stream[:16].tolist()))
+    # a random permutation works as well (the kernels never rely on a particular order)
+    rng = np.random.default_rng(1)
+    perm2 = cn.permute_channels(fd, rng.permutation(64), rng.permutation(64))
+    with torch.no_grad():
+        assert (forward_folded(perm2, x) - a).abs().max().item() < 2e-5
+
+
+def test_blob_sizes_match_the_library(cn, pkg, ng):
+    import __graft_entry__ as ge
+
+    ge.build()
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    lib.b2048_convnet_blob_bytes.restype = ctypes.c_int64
+    fd = cn.fold_state_dict(state_dict_from_golden(ng, "random"))
+    cal = ng["lg_boards"][:512]
+    for name, code in pkg.network.PRECISIONS.items():
+        blob = cn.pack_blob(fd, name, cal if name == "fp16x2" else None)
+        nbytes = blob.numel() * blob.element_size()
+        assert nbytes == lib.b2048_convnet_blob_bytes(code), name
+    with pytest.raises(ValueError):
+        cn.pack_blob(fd, "fp16x2")  # the precise image needs calibration boards
+    with pytest.raises(ValueError):
+        cn.pack_blob(fd, "int8")
