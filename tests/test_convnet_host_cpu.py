@@ -87,3 +87,60 @@ def test_blob_sizes_match_the_library(cn, pkg, ng):
         cn.pack_blob(fd, "fp16x2")  # the precise image needs calibration boards
     with pytest.raises(ValueError):
         cn.pack_blob(fd, "int8")
+
+
+def test_precise_mode_arithmetic_model_meets_the_bar(cn, orc, ng, lg100k):
+    """The precise tensor-core mode as the kernel computes it (csrc/convnet_tc.cuh: L0 exact, fp16 activations after every
+    epilogue, weight corrections on L1..L3 and activation corrections on L1..L2 over the first 32 channels of the calibrated
+    order), emulated in fp32 on 15,000 fixture boards: inside the north-star's 1e-2 with the calibrated order, not without it.
+    (tools/precision_study3.py runs the same model on all 150,371 boards: 0.0078; the B200 measures 0.0077.)"""
+    import torch.nn.functional as F
+
+    fd = cn.fold_state_dict(state_dict_from_golden(ng, "shipped"))
+    # calibration positions as network.calibration_boards builds them on the GPU, here with the oracle's engine
+    n, seed, depth_max = 2048, 0x2048CA11, 160
+    keys = np.array([orc.rng_key(seed, g) for g in range(n)], np.uint64)
+    boards = np.array([orc.init_board(int(k)) for k in keys], np.uint64)
+    scores, sidx, alive = np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.ones(n, np.uint8)
+    prio = np.tile(np.array([0, 1, 3, 2], np.uint8), (n, 1))
+    depth = (np.arange(n) * 7919) % depth_max
+    cal = boards.copy()
+    for step in range(1, depth_max):
+        orc.policy_step(boards, scores, sidx, keys, prio, alive)
+        cal = np.where(depth == step, boards, cal)
+    stream, mid = cn.split_channel_order(fd, cal)
+
+    r16 = lambda t: t.half().float()  # noqa: E731
+
+    def emulate(net, x, nch=32, w_layers=(1, 2, 3), a_layers=(1, 2)):
+        t = lambda a: torch.from_numpy(np.asarray(a, np.float32))  # noqa: E731
+        w, b = [t(a) for a in net["conv_w"]], [t(a).view(1, -1, 1, 1) for a in net["conv_b"]]
+
+        def conv(l, xin):
+            wh, xh = r16(w[l]), r16(xin)
+            y = F.conv2d(xh, wh, padding=1)
+            if l in a_layers:
+                y = y + F.conv2d(r16(xin - xh)[:, :nch], wh[:, :nch], padding=1)
+            if l in w_layers:
+                y = y + F.conv2d(xh[:, :nch], r16(w[l] - wh)[:, :nch], padding=1)
+            return y + b[l]
+
+        x = F.relu(F.conv2d(x, w[0], padding=1) + b[0])
+        for blk in range(3):
+            h = F.relu(conv(1 + 2 * blk, x))
+            x = F.relu(conv(2 + 2 * blk, h) + r16(x))
+            if blk < 2 and (3 + 2 * blk) not in a_layers:
+                x = r16(x)
+        x = F.relu(F.conv2d(x, t(net["head_w"]).view(4, 64, 1, 1)) + t(net["head_b"]).view(1, -1, 1, 1))
+        return F.log_softmax(F.linear(x.reshape(-1, 64), t(net["fc_w"]), t(net["fc_b"])), 1)
+
+    m = 15000
+    x = torch.from_numpy(cn.onehot_np(lg100k["boards"][:m]))
+    ref = torch.from_numpy(lg100k["lg_shipped"][:m])
+    with torch.no_grad():
+        ordered = (emulate(cn.permute_channels(fd, stream, mid), x) - ref).abs().max(1).values
+        unordered = (emulate(fd, x) - ref).abs().max(1).values
+        plain = (emulate(fd, x, w_layers=(), a_layers=()) - ref).abs().max(1).values
+    assert ordered.max().item() < 7e-3, ordered.max().item()          # full fixture: 0.0078
+    assert unordered.max().item() > 1.3 * ordered.max().item()        # the first 32 channels of the checkpoint's own order do not do it
+    assert plain.max().item() > 2.0 * ordered.max().item()            # one fp16 product per MAC: the throughput mode
