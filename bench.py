@@ -9,6 +9,14 @@ inside one persistent kernel) over one batch of `--games` synthetic fresh start 
 Per-GPU work is fixed as N grows ("weak"); the path shards by game with no data-path
 collective -- ranks only exchange their move counts and times for the report.
 
+Blocks of the line besides the contract's keys: `roofline.executed` (thread-instructions per move and pipe utilisation from the
+committed ncu capture, and `measured_pipe_rates`: this GPU's LOP3 / LOP3+IMAD rates measured in the run); `nn_policy` = the second
+half of the metric (K pipelined mcts_nn root evaluations, 256 origins per GPU, with `e2e`, `roofline`, `cpu_baseline`,
+`forward_only` + `torch_baseline` (config 5 point and the same-GPU PyTorch arms) and `precise_mode`: the tensor-core mode that
+keeps every board within 1e-2 of fp32 -- forward, root evaluation, the same K-evaluation loop over all ranks, config 3);
+`mcts_nn_game` = config 3 (one main game, ms per mcts_nn(number=50) main move); `selfplay256` = config 4 (256 main games in
+total, strong scaling); `train_step`; `mcts_fixed_game` = config 1.
+
 `--impl reference` times the CPU implementation of the same path on the box's host cores.  The
 reference is pure Python (no compiled part), so the arm runs the C restatement in oracle/
 (kind "port") on all host threads -- a faster baseline than the Python original.
